@@ -1,0 +1,253 @@
+/*
+ * pvraft_b200 -- C ABI of the B200-native (sm_100a) PV-RAFT hot path.
+ *
+ * The reference (weiyithu/PV-RAFT) has no FFI layer: its boundary is the Python nn.Module API
+ * (SURVEY.md section 8b).  This header is the drop-in boundary underneath that API: every entry
+ * point below replaces the ATen / torch-scatter op sequence of one reference function, cited as
+ * `file:line` relative to the reference tree.  The Python mirror of the reference modules
+ * (pvraft_b200/*.py, model/*.py) binds these symbols with ctypes -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.  `stream` is a cudaStream_t
+ *     passed as void*.  All pointers are DEVICE pointers on the current device.
+ *   - Every call is asynchronous on `stream`, allocates nothing, never synchronises, keeps no
+ *     state between calls (re-entrant); the caller owns every buffer.
+ *   - Return value: 0 = ok; < 0 = pvraft_status (argument / capability error, nothing launched);
+ *     > 0 = cudaError_t of the failed launch.  pvraft_last_error_string() describes the last
+ *     non-zero return on the calling thread.
+ *   - Tensors are contiguous fp32 unless stated.  Point-major layout [B,N,C] is used for every
+ *     per-point feature array (one point's channels are contiguous), coordinates are [B,N,3].
+ *   - GroupNorm statistics travel as raw double-precision sums ("stats": [B,8,2] = per sample,
+ *     per group (sum, sum of squares)); producers ACCUMULATE with atomics, so the caller zeroes
+ *     them (cudaMemsetAsync) before the producing call.
+ *   - Weights are passed in the reference's own state_dict layouts ([Cout,Cin(,1(,1))] row-major).
+ */
+#ifndef PVRAFT_B200_H
+#define PVRAFT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVRAFT_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define PVRAFT_API __attribute__((visibility("default")))
+#else
+#define PVRAFT_API
+#endif
+
+typedef enum pvraft_status {
+    PVRAFT_OK = 0,
+    PVRAFT_ERR_BAD_ARG = -1,     /* null pointer, non-positive size ... */
+    PVRAFT_ERR_UNSUPPORTED = -2, /* shape outside what the kernels are built for */
+    PVRAFT_ERR_SMEM = -3         /* working set does not fit the 227 KB shared memory of an SM */
+} pvraft_status;
+
+#define PVRAFT_KNN 32        /* model/corr.py:9, model/extractor.py:9 -- hard-coded in the reference */
+#define PVRAFT_GN_GROUPS 8   /* model/corr.py:17,25 ; model/flot/gconv.py:27,30,33 */
+#define PVRAFT_MOMENTS 16    /* doubles per sample for the kNN-branch moment accumulator */
+
+PVRAFT_API int pvraft_version(void);
+PVRAFT_API const char* pvraft_last_error_string(void);
+/* number of SMs / max opt-in dynamic shared memory of the current device (plumbing for the host) */
+PVRAFT_API int pvraft_device_info(int* sm_count, int* smem_optin_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Correlation truncation: per-row top-K (sorted descending) of a dense correlation matrix.
+ * Replaces torch.topk(corr, k, dim=2, sorted=True) in CorrBlock.init_module, model/corr.py:37-40.
+ *   corr [B,N,M] -> val [B,N,K] f32, idx [B,N,K] int32 (column ids; ties: lowest column first)
+ * Requires 32 <= K <= min(M, 1024); M*4 bytes must fit shared memory (M <= 49152).
+ * --------------------------------------------------------------------------------------------- */
+PVRAFT_API int pvraft_corr_topk_fwd(const float* corr, int B, int N, int M, int K, float* val, int32_t* idx, void* stream);
+
+/* xyz [B,N,3] -> [B,N,4] (w = 0): the float4 gather table used by pvraft_corr_lookup_fwd. */
+PVRAFT_API int pvraft_pad_xyz(const float* xyz, int64_t num_points, float* xyz4, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Point-voxel correlation lookup (index + reduce part), one fused pass over the K candidates of
+ * every point.  Replaces CorrBlock.get_voxel_feature up to (not incl.) out_conv, model/corr.py:47-71,
+ * and CorrBlock.get_knn_feature up to (not incl.) knn_conv, model/corr.py:75-91.
+ *   corr_val [B,N,K] f32, corr_idx [B,N,K] int32 (rows of xyz2), xyz2p [B,N,4], coords [B,N,3]
+ *   -> vox      [B,N,levels*27]  channel = level*27 + cell; mean corr of the candidates whose
+ *                                round((xyz-coords)/r_level) lies in {-1,0,1}^3  (round-half-even,
+ *                                true fp32 division; r_level = base_scale * 2^level)
+ *   -> knn_sel  [B,N,32,4]       (corr, dx, dy, dz) of the 32 candidates nearest to coords
+ *                                (distance = (dx*dx+dy*dy)+dz*dz, no FMA); order within a point is
+ *                                unspecified, exact-distance ties at the 32nd place: lowest slot
+ *   -> knn_slot [B,N,32] int32   candidate slot (0..K-1) of each selected neighbour; may be NULL
+ *   -> moments  [B,16] double    ACCUMULATED first/second moments of the 4-vector over the sample's
+ *                                N*32 edges: [0..3]=sum f_i, [4..13]=sum f_i f_j (i<=j, row-major
+ *                                upper triangle), [14]=edge count; may be NULL
+ *   -> dbg_cube [B,N,K,levels] int8  cell id or -1 of every candidate (test hook; NULL in production)
+ * K in {32,64,128,256,512,1024}; 1 <= levels <= 4; knn fixed at 32.
+ * --------------------------------------------------------------------------------------------- */
+PVRAFT_API int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr_idx, const float* xyz2p, const float* coords,
+                           int B, int N, int K, int levels, float base_scale, float* vox, float* knn_sel,
+                           int32_t* knn_slot, double* moments, int8_t* dbg_cube, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Generic fused (GroupNorm -> activation -> 1x1 conv [-> bias] [-> ReLU]) layer over points with
+ * GroupNorm statistics of the OUTPUT accumulated on the fly.  It is the dense building block of
+ * CorrBlock.out_conv[0] (model/corr.py:16), SetConv.fc2/fc3 and the fc1 pre-transform
+ * (model/flot/gconv.py:26-33,58-85), FlotRefine.fc (model/refine.py:14,21).
+ * --------------------------------------------------------------------------------------------- */
+typedef enum pvraft_in_mode {
+    PVRAFT_IN_PLAIN = 0,  /* x = in                                                     */
+    PVRAFT_IN_GN = 1,     /* x = act(GN(in))            using in_stats/in_gamma/in_beta  */
+    PVRAFT_IN_GN_MINMAX = 2 /* x = act(GN(in_max or in_min)): per channel picks max when the GN scale is >= 0,
+                               min otherwise (max-pool over neighbours commuted with the monotone GN+LeakyReLU) */
+} pvraft_in_mode;
+
+typedef enum pvraft_act {
+    PVRAFT_ACT_NONE = 0,
+    PVRAFT_ACT_RELU = 1,
+    PVRAFT_ACT_LRELU = 2 /* slope in act_slope (LeakyReLU 0.1, or PReLU with its learned slope) */
+} pvraft_act;
+
+typedef struct pvraft_linear_args {
+    const float* in;        /* [B,N,cin] (PLAIN/GN) or the per-channel max array (GN_MINMAX) */
+    const float* in_min;    /* [B,N,cin] per-channel min (GN_MINMAX only) */
+    const double* in_stats; /* [B,8,2] sums of the un-normalised input (GN modes) */
+    const float* in_gamma;  /* [cin] */
+    const float* in_beta;   /* [cin] */
+    double in_count;        /* number of elements per (sample, group) behind in_stats */
+    int in_mode;            /* pvraft_in_mode */
+    int in_act;             /* pvraft_act applied after the input GroupNorm */
+    float in_slope;
+    const float* weight;    /* [cout,cin] row-major; row stride w_ld floats (0 = cin): lets fc1.weight[:, :cin] be used in place */
+    int w_ld;
+    const float* bias;      /* [cout] or NULL */
+    const float* residual;  /* [B,N,cout] added to the output after bias/activation, or NULL (model/refine.py:22) */
+    int out_act;            /* pvraft_act applied to the output (NONE or RELU) */
+    float* out;             /* [B,N,cout] */
+    double* out_stats;      /* [B,8,2] ACCUMULATED sums of `out`, or NULL (cout % 8 == 0 required) */
+    int B, N, cin, cout;
+} pvraft_linear_args;
+
+PVRAFT_API int pvraft_linear_fwd(const pvraft_linear_args* a, void* stream);
+
+/* out[B,N,C] (or channel-major [B,C,N] when transpose_out != 0) = act(GN(in)) -- the trailing
+ * GroupNorm+LeakyReLU of SetConv (model/flot/gconv.py:33,82-83) when nothing follows it. */
+PVRAFT_API int pvraft_gn_act_fwd(const float* in, const double* stats, const float* gamma, const float* beta, double count,
+                      int act, float slope, int B, int N, int C, int transpose_out, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Correlation feature head (+ optional MotionEncoder), one persistent kernel.
+ *  feature stage (when y1 != NULL): out_conv[1:] on the voxel branch + knn_conv/max/knn_out on the
+ *    kNN branch, summed.  Replaces model/corr.py:17-19 (GN, PReLU, Conv1d 128->64), :24-29,:91-93, :45.
+ *      y1 [B,N,128] = out_conv[0] output (pvraft_linear_fwd) with y1_stats [B,8,2];
+ *      knn_sel [B,N,32,4], moments [B,16] from pvraft_corr_lookup_fwd  -> corr_feat [B,N,64] (may be NULL)
+ *  motion stage (when motion != NULL): MotionEncoder.forward, model/update.py:15-21, on the feature
+ *    just computed (or on corr_in [B,N,64] when y1 == NULL) and flow [B,N,3] -> motion [B,N,64]
+ *    (channels 0..60 learned, 61..63 = flow).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct pvraft_corrfeat_args {
+    const float* y1;
+    const double* y1_stats;
+    const float* gn1_gamma; /* corr_block.out_conv.1.weight [128] */
+    const float* gn1_beta;  /* corr_block.out_conv.1.bias   [128] */
+    const float* prelu1;    /* corr_block.out_conv.2.weight [1]   */
+    const float* w_out;     /* corr_block.out_conv.3.weight [64,128] */
+    const float* b_out;     /* corr_block.out_conv.3.bias   [64]  */
+    const float* knn_sel;
+    const double* moments;
+    const float* w_knn;     /* corr_block.knn_conv.0.weight [64,4] */
+    const float* b_knn;     /* corr_block.knn_conv.0.bias   [64]   */
+    const float* gnk_gamma; /* corr_block.knn_conv.1.weight [64]   */
+    const float* gnk_beta;  /* corr_block.knn_conv.1.bias   [64]   */
+    const float* preluk;    /* corr_block.knn_conv.2.weight [1]    */
+    const float* w_kout;    /* corr_block.knn_out.weight [64,64]   */
+    const float* b_kout;    /* corr_block.knn_out.bias   [64]      */
+    float* corr_feat;       /* [B,N,64] or NULL */
+    const float* corr_in;   /* [B,N,64], used only when y1 == NULL */
+    const float* flow;      /* [B,N,3] */
+    const float* w_cc; const float* b_cc;   /* update_block.motion_encoder.conv_corr [64,64],[64] */
+    const float* w_cf; const float* b_cf;   /* update_block.motion_encoder.conv_flow [64,3],[64]  */
+    const float* w_cm; const float* b_cm;   /* update_block.motion_encoder.conv      [61,128],[61] */
+    float* motion;          /* [B,N,64] or NULL */
+    int B, N;
+} pvraft_corrfeat_args;
+
+PVRAFT_API int pvraft_corr_feature_fwd(const pvraft_corrfeat_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * ConvGRU.  Replaces model/update.py:31-40 with x = [inp, motion] (update.py:84).
+ *   net, inp, motion [B,N,64] -> net_out [B,N,64]   (net_out may alias net)
+ * --------------------------------------------------------------------------------------------- */
+typedef struct pvraft_gru_args {
+    const float* net;
+    const float* inp;
+    const float* motion;
+    const float* w_z; const float* b_z;     /* update_block.gru.convz [64,192],[64] */
+    const float* w_r; const float* b_r;     /* update_block.gru.convr */
+    const float* w_q; const float* b_q;     /* update_block.gru.convq */
+    float* net_out;
+    int B, N;
+} pvraft_gru_args;
+
+PVRAFT_API int pvraft_gru_fwd(const pvraft_gru_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SetConv edge stage: per point, over its 32 graph neighbours j:  y_e = P_j - P_i + W_e . (x_j - x_i)
+ * (x = point coordinates; x_j - x_i is the graph's edge feature), reduced to per-channel max and min over the neighbours, with the
+ * GroupNorm statistics of all N*32*C pre-activation values accumulated.  Replaces the gather +
+ * fc1 + (statistics of) gn1 + max-pool of SetConv.forward, model/flot/gconv.py:65-80.
+ *   fc1p [B,N,C], nbr [B,N,32] int32 (LOCAL neighbour ids), edge_feats [B,N,32,3] (= graph.edge_feats),
+ *   w_fc1 [C,cin+3] (columns cin..cin+2 are read)
+ *   -> ymax, ymin [B,N,C]; stats [B,8,2] accumulated.   C % 8 == 0, C <= 128.
+ * --------------------------------------------------------------------------------------------- */
+PVRAFT_API int pvraft_setconv_edge_fwd(const float* fc1p, const int32_t* nbr, const float* edge_feats, const float* w_fc1, int cin,
+                            int B, int N, int C, float* ymax, float* ymin, double* stats, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * FlowHead output stage + RAFT coordinate update.  Replaces model/update.py:69,71-72 (conv1, cat,
+ * out_conv) after the SetConv's last GroupNorm+LeakyReLU (gconv.py:82-83), and
+ * model/RAFTSceneFlow.py:45-46 (coords2 += delta; flow = coords2 - coords1).
+ *   z3 [B,N,64] (setconv.fc3 output) + z3_stats, net [B,N,64], coords1/coords2 [B,N,3]
+ *   -> delta [B,N,3], coords2_out [B,N,3] (may alias coords2), flow_out [B,N,3] (may be NULL)
+ * --------------------------------------------------------------------------------------------- */
+typedef struct pvraft_flowout_args {
+    const float* z3;
+    const double* z3_stats;
+    const float* gn3_gamma; const float* gn3_beta; /* setconv.gn3 [64] */
+    const float* net;
+    const float* w_c1; const float* b_c1;          /* flow_head.conv1 [64,64],[64] */
+    const float* w_o0; const float* b_o0;          /* flow_head.out_conv.0 [64,128],[64] */
+    const float* w_o2; const float* b_o2;          /* flow_head.out_conv.2 [3,64],[3] */
+    const float* coords1;
+    const float* coords2;
+    float* delta;
+    float* coords2_out;
+    float* flow_out;
+    int B, N;
+} pvraft_flowout_args;
+
+PVRAFT_API int pvraft_flow_out_fwd(const pvraft_flowout_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Brute-force k nearest neighbours.  Backs knn_point (model/pointconv.py:28-39) and the adjacency
+ * of Graph.construct_graph (model/flot/graph.py:53-60, which argsorts a full N x N matrix).
+ *   xyz [B,N,3] (candidates), query [B,S,3] -> idx [B,S,k] int32 LOCAL candidate ids, unordered;
+ *   rel [B,S,k,3] = xyz[idx] - query (the graph's edge features, graph.py:69-74), or NULL.
+ * mode 0: distance = (|q|^2 + |x|^2) - 2 q.x      (graph.py:53-57 op order)
+ * mode 1: distance = (-2 q.x + |q|^2) + |x|^2     (pointconv.py:21-24 op order)
+ * with q.x = fma(qz,xz, fma(qy,xy, qx*xx)) and |.|^2 = (x*x+y*y)+z*z.  1 <= k <= 32, N >= k.
+ * Ties at the k-th place: lowest candidate id.
+ * --------------------------------------------------------------------------------------------- */
+PVRAFT_API int pvraft_knn_fwd(const float* xyz, const float* query, int B, int N, int S, int k, int mode, int32_t* idx,
+                   float* rel, void* stream);
+
+/* sizeof() of the argument structs as compiled into the library (0 = linear, 1 = corrfeat, 2 = gru,
+ * 3 = flowout; -1 otherwise): lets a foreign-language binding verify its struct layout at load time. */
+PVRAFT_API int pvraft_sizeof(int which);
+
+/* [B,C,N] <-> [B,N,C] transposes used at the reference-layout seams of the Python modules. */
+PVRAFT_API int pvraft_transpose_fwd(const float* in, int B, int R, int C, float* out, void* stream); /* [B,R,C] -> [B,C,R] */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVRAFT_B200_H */

@@ -1,0 +1,144 @@
+"""CorrBlock -- mirror of the reference module (model/corr.py:8-100): same constructor, parameters,
+state_dict keys and call surface (`init_module`, `__call__(coords)`, `get_voxel_feature`,
+`get_knn_feature`, `calculate_corr`), with the arithmetic on the B200 kernels.
+
+State layout differs from the reference on purpose: instead of the materialised
+`truncate_xyz2 [B,N,K,3]` (12 B/candidate) the block keeps the candidate INDEX (int32) next to the
+correlation value -- 8 B per candidate per iteration is the whole HBM stream of the lookup kernel;
+xyz is gathered from a 16 B/point table staged in shared memory.  `truncated_corr` and
+`truncate_xyz2` stay available as attributes/properties for API parity.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .ops import ACT_NONE
+
+
+def _w(p):
+    return p.detach()
+
+
+class CorrBlock(nn.Module):
+    def __init__(self, num_levels=3, base_scale=0.25, resolution=3, truncate_k=128, knn=32):
+        super().__init__()
+        if resolution != 3:
+            raise NotImplementedError('the lookup kernel implements the 3x3x3 cube the reference uses (resolution=3)')
+        if knn != ops.KNN:
+            raise NotImplementedError('the lookup kernel selects 32 neighbours (model/corr.py:9)')
+        self.truncate_k = truncate_k
+        self.num_levels = num_levels
+        self.resolution = resolution
+        self.base_scale = base_scale
+        self.out_conv = nn.Sequential(
+            nn.Conv1d((self.resolution ** 3) * self.num_levels, 128, 1),
+            nn.GroupNorm(8, 128),
+            nn.PReLU(),
+            nn.Conv1d(128, 64, 1),
+        )
+        self.knn = knn
+        self.knn_conv = nn.Sequential(
+            nn.Conv2d(4, 64, 1),
+            nn.GroupNorm(8, 64),
+            nn.PReLU(),
+        )
+        self.knn_out = nn.Conv1d(64, 64, 1)
+        self.truncated_corr = None
+        self.corr_idx = None
+        self.xyz2p = None
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def calculate_corr(fmap1, fmap2):
+        """model/corr.py:95-100.  A plain library GEMM (cuBLAS via torch.matmul) -- the dense N x N
+        product is the one genuine large contraction of the model; fusing it with the top-K
+        selection in a tcgen05 kernel is the next step."""
+        dim = fmap1.shape[1]
+        corr = torch.matmul(fmap1.transpose(1, 2), fmap2)
+        return corr / torch.sqrt(torch.tensor(dim).float())
+
+    def init_module(self, fmap1, fmap2, xyz2):
+        """model/corr.py:31-42: build the truncated correlation state for one forward pass."""
+        b, n_p, _ = xyz2.shape
+        if n_p < self.truncate_k:
+            raise ValueError(f'truncate_k={self.truncate_k} exceeds the number of points {n_p}')
+        corr = self.calculate_corr(fmap1.detach().float(), fmap2.detach().float()).contiguous()
+        self.truncated_corr, self.corr_idx = ops.corr_topk(corr, self.truncate_k)
+        self._xyz2 = xyz2.detach().contiguous().float()
+        self.xyz2p = ops.pad_xyz(self._xyz2)
+
+    def set_state(self, truncated_corr, corr_idx, xyz2):
+        """Install an externally built state (tests / benchmarks): corr [B,N,K] f32, idx [B,N,K] int."""
+        self.truncated_corr = truncated_corr.contiguous().float()
+        self.corr_idx = corr_idx.contiguous().to(torch.int32)
+        self._xyz2 = xyz2.contiguous().float()
+        self.xyz2p = ops.pad_xyz(self._xyz2)
+
+    @property
+    def truncate_xyz2(self):
+        """[B,N,K,3] candidate coordinates, materialised on demand (model/corr.py:42)."""
+        b, n, k = self.corr_idx.shape
+        idx = self.corr_idx.long().reshape(b, n * k, 1).expand(b, n * k, 3)
+        return torch.gather(self._xyz2, 1, idx).reshape(b, n, k, 3)
+
+    @property
+    def ones_matrix(self):
+        return torch.ones_like(self.truncated_corr)
+
+    # ------------------------------------------------------------------------------------------
+    def lookup(self, coords, **kw):
+        """Index + reduce part of the lookup (pvraft_corr_lookup_fwd) -> dict(vox, knn_sel, moments, ...)."""
+        if self.truncated_corr is None:
+            raise RuntimeError('CorrBlock.init_module must run before the lookup')
+        return ops.corr_lookup(self.truncated_corr, self.corr_idx, self.xyz2p, coords.detach().contiguous().float(),
+                               self.num_levels, self.base_scale, **kw)
+
+    def feature_args(self, lk, y1, y1_stats, b, n):
+        oc, kc = self.out_conv, self.knn_conv
+        a = _lib.CorrFeatArgs()
+        a.y1, a.y1_stats = ops._p(y1), ops._p(y1_stats, torch.float64)
+        a.gn1_gamma, a.gn1_beta, a.prelu1 = ops._p(_w(oc[1].weight)), ops._p(_w(oc[1].bias)), ops._p(_w(oc[2].weight))
+        a.w_out, a.b_out = ops._p(_w(oc[3].weight)), ops._p(_w(oc[3].bias))
+        a.knn_sel, a.moments = ops._p(lk['knn_sel']), ops._p(lk['moments'], torch.float64)
+        a.w_knn, a.b_knn = ops._p(_w(kc[0].weight)), ops._p(_w(kc[0].bias))
+        a.gnk_gamma, a.gnk_beta, a.preluk = ops._p(_w(kc[1].weight)), ops._p(_w(kc[1].bias)), ops._p(_w(kc[2].weight))
+        a.w_kout, a.b_kout = ops._p(_w(self.knn_out.weight)), ops._p(_w(self.knn_out.bias))
+        a.B, a.N = b, n
+        return a
+
+    def feature_point_major(self, coords, motion_args=None):
+        """coords [B,N,3] -> correlation feature [B,N,64] (point-major).  `motion_args` lets
+        UpdateBlock fuse its MotionEncoder into the same launch (see update.py)."""
+        b, n, _ = coords.shape
+        lk = self.lookup(coords)
+        stats = ops.new_stats(b, coords.device, 1)
+        oc = self.out_conv
+        y1 = ops.linear(lk['vox'], _w(oc[0].weight), _w(oc[0].bias), out_stats=stats[0], out_act=ACT_NONE)
+        a = self.feature_args(lk, y1, stats[0], b, n)
+        corr = torch.empty(b, n, 64, dtype=torch.float32, device=coords.device)
+        a.corr_feat = ops._p(corr)
+        keep = [lk, y1, stats, corr]
+        if motion_args is not None:
+            motion_args(a, keep)
+        ops.corr_feature(a)
+        return corr, keep
+
+    def __call__(self, coords):
+        """model/corr.py:44-45 -> [B,64,N]."""
+        corr, _ = self.feature_point_major(coords)
+        return ops.transpose(corr)
+
+    # the two branches separately, for API parity with the reference (model/corr.py:47,75); each runs
+    # the fused kernels and zeroes the other branch by linearity of the final sum.
+    def get_voxel_feature(self, coords):
+        b, n, _ = coords.shape
+        lk = self.lookup(coords)
+        stats = ops.new_stats(b, coords.device, 1)
+        oc = self.out_conv
+        y1 = ops.linear(lk['vox'], _w(oc[0].weight), _w(oc[0].bias), out_stats=stats[0])
+        act = ops.gn_act(y1, stats[0], _w(oc[1].weight), _w(oc[1].bias), float(n) * 16, ops.ACT_LRELU,
+                         float(oc[2].weight.detach().reshape(-1)[0]))
+        return ops.transpose(ops.linear(act, _w(oc[3].weight), _w(oc[3].bias)))
+
+    def get_knn_feature(self, coords):
+        return self.__call__(coords) - self.get_voxel_feature(coords)

@@ -1,0 +1,129 @@
+// SetConv edge stage (reference model/flot/gconv.py:65-80): the gather over the 32-NN graph, fc1 on
+// [x_j - x_i, rel_xyz], the statistics of gn1 and the max-pool over neighbours, without ever
+// materialising the reference's [B, C+3, 32, N] edge tensor.
+//
+// fc1 is linear and bias-free, so  W.[x_j - x_i, e] = P_j - P_i + W_e.e  with  P = W[:, :cin].x  computed
+// once per point by pvraft_linear_fwd; this kernel only gathers the 32 rows P_j (L2-resident table).
+// GroupNorm + LeakyReLU is monotone per channel, so max_e lrelu(GN(y_e)) = lrelu(GN(max_e y_e)) when the
+// folded GN scale is >= 0 and lrelu(GN(min_e y_e)) otherwise: the kernel emits both the per-channel max
+// and min of the raw y, plus the double-precision (sum, sum^2) of all N*32*C raw values per group.
+//
+// One warp per point; lane l owns channels l, l+32, l+64, l+96 (coalesced 128-byte row segments).
+#include "common.cuh"
+
+namespace pvraft {
+
+constexpr int kEdgeThreads = 256;
+
+template <int SLOTS>
+__global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge(const float* __restrict__ fc1p, const int32_t* __restrict__ nbr,
+                                                               const float* __restrict__ edge_feats, const float* __restrict__ w_fc1,
+                                                               int cin, int B, int N, int C, float* __restrict__ ymax,
+                                                               float* __restrict__ ymin, double* __restrict__ stats) {
+    __shared__ double s_part[kEdgeThreads / 32][128][2];
+    const int lane = lane_id(), w = warp_id(), nwarps = kEdgeThreads / 32;
+    const int ld = cin + 3;
+    float wx[SLOTS], wy[SLOTS], wz[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const int c = lane + 32 * s;
+        wx[s] = c < C ? __ldg(w_fc1 + (size_t)c * ld + cin + 0) : 0.f;
+        wy[s] = c < C ? __ldg(w_fc1 + (size_t)c * ld + cin + 1) : 0.f;
+        wz[s] = c < C ? __ldg(w_fc1 + (size_t)c * ld + cin + 2) : 0.f;
+    }
+    const long long total = (long long)B * N;
+    long long pt_begin, pt_end;
+    split_range(total, gridDim.x, blockIdx.x, pt_begin, pt_end);
+    long long seg = pt_begin;
+    while (seg < pt_end) {
+        const int b = (int)(seg / N);
+        long long seg_end = (long long)(b + 1) * N;
+        if (seg_end > pt_end) seg_end = pt_end;
+        double dS[SLOTS], dSS[SLOTS];
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) { dS[s] = 0.0; dSS[s] = 0.0; }
+        const float* P = fc1p + (size_t)b * N * C;
+        for (long long pt = seg + w; pt < seg_end; pt += nwarps) {
+            const int i = (int)(pt - (long long)b * N);
+            const int my_nbr = __ldg(nbr + pt * 32 + lane);
+            // lane e fetches the edge feature of neighbour e (graph.edge_feats = x_j - x_i, gconv.py:66)
+            const float* ef = edge_feats + ((size_t)pt * 32 + lane) * 3;
+            const float rx = __ldg(ef), ry = __ldg(ef + 1), rz = __ldg(ef + 2);
+            float pi[SLOTS], mx[SLOTS], mn[SLOTS], s1[SLOTS], s2[SLOTS];
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const int c = lane + 32 * s;
+                pi[s] = c < C ? __ldg(P + (size_t)i * C + c) : 0.f;
+                mx[s] = -INFINITY; mn[s] = INFINITY; s1[s] = 0.f; s2[s] = 0.f;
+            }
+#pragma unroll 4
+            for (int e = 0; e < 32; ++e) {
+                const int j = __shfl_sync(kFull, my_nbr, e);
+                const float ex = __shfl_sync(kFull, rx, e), ey = __shfl_sync(kFull, ry, e), ez = __shfl_sync(kFull, rz, e);
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    const int c = lane + 32 * s;
+                    if (c < C) {
+                        const float pj = __ldg(P + (size_t)j * C + c);
+                        const float y = (pj - pi[s]) + fmaf(wz[s], ez, fmaf(wy[s], ey, wx[s] * ex));
+                        mx[s] = fmaxf(mx[s], y);
+                        mn[s] = fminf(mn[s], y);
+                        s1[s] += y;
+                        s2[s] = fmaf(y, y, s2[s]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const int c = lane + 32 * s;
+                if (c < C) {
+                    ymax[(size_t)pt * C + c] = mx[s];
+                    ymin[(size_t)pt * C + c] = mn[s];
+                    dS[s] += (double)s1[s];
+                    dSS[s] += (double)s2[s];
+                }
+            }
+        }
+        // block reduction of the per-channel partials -> per-group sums -> one atomic per (group, moment)
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            s_part[w][lane + 32 * s][0] = dS[s];
+            s_part[w][lane + 32 * s][1] = dSS[s];
+        }
+        __syncthreads();
+        if (threadIdx.x < 16) {
+            const int g = threadIdx.x >> 1, m = threadIdx.x & 1, gsz = C / PVRAFT_GN_GROUPS;
+            double acc = 0.0;
+            for (int c = g * gsz; c < (g + 1) * gsz; ++c)
+                for (int ww = 0; ww < nwarps; ++ww) acc += s_part[ww][c][m];
+            if (acc != 0.0) atomicAdd(stats + (size_t)b * 16 + threadIdx.x, acc);
+        }
+        seg = seg_end;
+    }
+}
+
+}  // namespace pvraft
+
+using namespace pvraft;
+
+extern "C" int pvraft_setconv_edge_fwd(const float* fc1p, const int32_t* nbr, const float* edge_feats, const float* w_fc1, int cin,
+                                       int B, int N, int C, float* ymax, float* ymin, double* stats, void* stream) {
+    if (!fc1p || !nbr || !edge_feats || !w_fc1 || !ymax || !ymin || !stats) return fail(PVRAFT_ERR_BAD_ARG, "setconv_edge: null pointer");
+    if (B <= 0 || N <= 0 || cin <= 0) return fail(PVRAFT_ERR_BAD_ARG, "setconv_edge: bad shape");
+    if (C <= 0 || C > 128 || C % PVRAFT_GN_GROUPS) return fail(PVRAFT_ERR_UNSUPPORTED, "setconv_edge: C=%d (multiple of 8, <= 128)", C);
+    const long long total = (long long)B * N;
+    long long g = (long long)sm_count() * 8;
+    const long long need = (total + (kEdgeThreads / 32) - 1) / (kEdgeThreads / 32);
+    if (g > need) g = need;
+    const int grid = (int)(g < 1 ? 1 : g);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int slots = (C + 31) / 32;
+    switch (slots) {
+        case 1: k_setconv_edge<1><<<grid, kEdgeThreads, 0, st>>>(fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats); break;
+        case 2: k_setconv_edge<2><<<grid, kEdgeThreads, 0, st>>>(fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats); break;
+        case 3: k_setconv_edge<3><<<grid, kEdgeThreads, 0, st>>>(fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats); break;
+        default: k_setconv_edge<4><<<grid, kEdgeThreads, 0, st>>>(fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats); break;
+    }
+    return check_launch("setconv_edge");
+}

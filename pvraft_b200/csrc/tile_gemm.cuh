@@ -1,0 +1,71 @@
+// Register-tiled fp32 point-MLP building block shared by the dense kernels.
+//
+// A CTA of 256 threads owns a tile of TP = 64 points.  Activations sit in shared memory
+// point-major ([point][k], row stride AS floats, AS % 4 == 0 and (AS/4) odd so that the 16-byte
+// words of consecutive rows land in different banks), weights k-major ([k][channel], stride WS).
+// Thread (tx = tid & 15, ty = tid >> 4) accumulates a 4-point x (4*CM4)-channel register tile:
+// points ty*4 .. ty*4+3, channels tx*4 + 64*g .. +3 for g < CM4.  The k loop runs in chunks of 4
+// with 128-bit shared loads for both operands (activation words are warp-broadcast: a warp spans
+// only two ty values).
+#pragma once
+#include "common.cuh"
+
+namespace pvraft {
+
+constexpr int kTP = 64;          // points per tile
+constexpr int kMlpThreads = 256; // threads per CTA of the dense kernels
+
+template <int CM4>
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ act, int AS, const float* __restrict__ w, int WS,
+                                          int KD, float (&acc)[4][CM4 * 4]) {
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const float* a0 = act + (ty * 4) * AS;
+    const float* w0 = w + tx * 4;
+#pragma unroll 2
+    for (int k = 0; k < KD; k += 4) {
+        float4 a[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) a[p] = *reinterpret_cast<const float4*>(a0 + p * AS + k);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int g = 0; g < CM4; ++g) {
+                const float4 wv = *reinterpret_cast<const float4*>(w0 + (k + kk) * WS + g * 64);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float av = kk == 0 ? a[p].x : kk == 1 ? a[p].y : kk == 2 ? a[p].z : a[p].w;
+                    acc[p][g * 4 + 0] = fmaf(av, wv.x, acc[p][g * 4 + 0]);
+                    acc[p][g * 4 + 1] = fmaf(av, wv.y, acc[p][g * 4 + 1]);
+                    acc[p][g * 4 + 2] = fmaf(av, wv.z, acc[p][g * 4 + 2]);
+                    acc[p][g * 4 + 3] = fmaf(av, wv.w, acc[p][g * 4 + 3]);
+                }
+            }
+        }
+    }
+}
+
+// Stage a [cout][cin] row-major global weight as k-major [KD][WS] in shared memory, zero padded
+// (rows cin..KD-1 and columns cout..WS-1 are zero).  `col0` selects a sub-range of input columns.
+__device__ __forceinline__ void stage_weight(float* __restrict__ dst, int KD, int WS, const float* __restrict__ src,
+                                             int cout, int cin_total, int col0, int cin) {
+    for (int i = threadIdx.x; i < KD * WS; i += blockDim.x) {
+        const int k = i / WS, c = i - k * WS;
+        dst[i] = (k < cin && c < cout) ? __ldg(src + (size_t)c * cin_total + col0 + k) : 0.f;
+    }
+}
+
+__device__ __forceinline__ void stage_vector(float* __restrict__ dst, int n_pad, const float* __restrict__ src, int n) {
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) dst[i] = (src != nullptr && i < n) ? __ldg(src + i) : 0.f;
+}
+
+// padded activation row stride: multiple of 4 floats with an odd number of 16-byte words
+__host__ __device__ __forceinline__ int act_stride(int k_pad) {
+    int s = k_pad + 4;
+    if (((s / 4) & 1) == 0) s += 4;
+    return s;
+}
+
+__host__ __device__ __forceinline__ int pad4(int x) { return (x + 3) & ~3; }
+__host__ __device__ __forceinline__ int pad64(int x) { return (x + 63) & ~63; }
+
+}  // namespace pvraft

@@ -1,0 +1,68 @@
+"""SetConv -- mirror of the reference module (model/flot/gconv.py:4-85), same parameters and
+state_dict keys (fc1/gn1/fc2/gn2/fc3/gn3), forward on the B200 kernels."""
+import torch
+
+from . import ops
+from .ops import ACT_LRELU, IN_GN, IN_GN_MINMAX
+
+
+class Deferred:
+    """A SetConv output whose last GroupNorm+LeakyReLU has not been applied yet: the next consumer
+    folds it into its own input staging (pvraft_linear_fwd IN_GN mode)."""
+
+    def __init__(self, z, stats, gamma, beta, count):
+        self.z, self.stats, self.gamma, self.beta, self.count = z, stats, gamma, beta, count
+
+    def materialize(self, transpose_out=False):
+        return ops.gn_act(self.z, self.stats, self.gamma, self.beta, self.count, ACT_LRELU, 0.1, transpose_out)
+
+
+def _w(p):
+    return p.detach()
+
+
+class SetConv(torch.nn.Module):
+    def __init__(self, nb_feat_in, nb_feat_out):
+        super().__init__()
+        # model/flot/gconv.py:21-24
+        mid = nb_feat_out // 2 if nb_feat_in % 2 != 0 else (nb_feat_out + nb_feat_in) // 2
+        self.nb_feat_in, self.nb_feat_out, self.mid = nb_feat_in, nb_feat_out, mid
+        self.fc1 = torch.nn.Conv2d(nb_feat_in + 3, mid, 1, bias=False)
+        self.gn1 = torch.nn.GroupNorm(8, mid, affine=True)
+        self.fc2 = torch.nn.Conv1d(mid, nb_feat_out, 1, bias=False)
+        self.gn2 = torch.nn.GroupNorm(8, nb_feat_out, affine=True)
+        self.fc3 = torch.nn.Conv1d(nb_feat_out, nb_feat_out, 1, bias=False)
+        self.gn3 = torch.nn.GroupNorm(8, nb_feat_out, affine=True)
+
+    def forward_deferred(self, signal, graph):
+        """signal: [B,N,cin] tensor or a Deferred from the previous SetConv -> Deferred."""
+        cin, mid, cout = self.nb_feat_in, self.mid, self.nb_feat_out
+        if isinstance(signal, Deferred):
+            z = signal.z
+            b, n, _ = z.shape
+            stats = ops.new_stats(b, z.device, 3)
+            # fc1 pre-transform P = fc1.weight[:, :cin] . lrelu(gn3_prev(z_prev))   (gconv.py:65-73)
+            p = ops.linear(z, _w(self.fc1.weight), cin=cin, w_ld=cin + 3, in_mode=IN_GN, in_stats=signal.stats,
+                           in_gamma=signal.gamma, in_beta=signal.beta, in_count=signal.count, in_act=ACT_LRELU,
+                           in_slope=0.1, cout=mid)
+        else:
+            x = signal.detach().contiguous().float()
+            b, n, _ = x.shape
+            stats = ops.new_stats(b, x.device, 3)
+            p = ops.linear(x, _w(self.fc1.weight), cin=cin, w_ld=cin + 3, cout=mid)
+        if graph.size[0] // b != n:
+            raise ValueError('graph and signal disagree on the number of points')
+        ymax, ymin = ops.setconv_edge(p, graph.nbr, graph._rel, _w(self.fc1.weight), cin, stats[0])
+        gsz1 = mid // 8
+        z2 = ops.linear(ymax, _w(self.fc2.weight), in_mode=IN_GN_MINMAX, in_min=ymin, in_stats=stats[0],
+                        in_gamma=_w(self.gn1.weight), in_beta=_w(self.gn1.bias), in_count=float(n) * 32 * gsz1,
+                        in_act=ACT_LRELU, in_slope=0.1, out_stats=stats[1])
+        gsz = cout // 8
+        z3 = ops.linear(z2, _w(self.fc3.weight), in_mode=IN_GN, in_stats=stats[1], in_gamma=_w(self.gn2.weight),
+                        in_beta=_w(self.gn2.bias), in_count=float(n) * gsz, in_act=ACT_LRELU, in_slope=0.1,
+                        out_stats=stats[2])
+        return Deferred(z3, stats[2], _w(self.gn3.weight), _w(self.gn3.bias), float(n) * gsz)
+
+    def forward(self, signal, graph):
+        """signal [B,N,cin], graph -> [B,N,cout]   (model/flot/gconv.py:38-85)."""
+        return self.forward_deferred(signal, graph).materialize()

@@ -1,0 +1,150 @@
+"""Tensor-level wrappers over the C ABI (include/pvraft_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream; every arithmetic step of the
+hot path happens inside libpvraft_b200.so.  All wrappers require contiguous CUDA tensors and raise
+on anything else -- there is deliberately no CPU / eager fallback.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, IN_GN, IN_GN_MINMAX, IN_PLAIN, KNN, MOMENTS, check, lib)
+
+launch_count = 0   # C-ABI calls that launch a kernel (bench.py reports it as gpu_launches)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, dtype=torch.float32):
+    if t is None:
+        return None
+    if not torch.is_tensor(t):
+        raise TypeError(f'expected a tensor, got {type(t)}')
+    if not t.is_cuda:
+        raise _lib.PvraftError('pvraft_b200 kernels need CUDA tensors (no CPU fallback exists)')
+    if t.dtype != dtype:
+        raise TypeError(f'expected {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise ValueError('expected a contiguous tensor')
+    return t.data_ptr()
+
+
+def _count(rc, what):
+    global launch_count
+    check(rc, what)
+    launch_count += 1
+
+
+def new_stats(b, device, n=1):
+    """Zeroed GroupNorm accumulators: n x [B,8,2] doubles (one cudaMemset for all of them)."""
+    return torch.zeros(n, b, 8, 2, dtype=torch.float64, device=device)
+
+
+def pad_xyz(xyz):
+    b, n, _ = xyz.shape
+    out = torch.empty(b, n, 4, dtype=torch.float32, device=xyz.device)
+    _count(lib().pvraft_pad_xyz(_p(xyz), b * n, _p(out), _stream()), 'pad_xyz')
+    return out
+
+
+def corr_topk(corr, k):
+    """corr [B,N,M] -> (val [B,N,K] f32 sorted desc, idx [B,N,K] int32)."""
+    b, n, m = corr.shape
+    val = torch.empty(b, n, k, dtype=torch.float32, device=corr.device)
+    idx = torch.empty(b, n, k, dtype=torch.int32, device=corr.device)
+    _count(lib().pvraft_corr_topk_fwd(_p(corr), b, n, m, k, _p(val), _p(idx, torch.int32), _stream()), 'corr_topk')
+    return val, idx
+
+
+def corr_lookup(corr_val, corr_idx, xyz2p, coords, levels, base_scale, vox=None, knn_sel=None, moments=None,
+                want_slots=False, want_cube=False):
+    """-> dict(vox [B,N,levels*27], knn_sel [B,N,32,4], moments [B,16] f64, [knn_slot], [cube])."""
+    b, n, k = corr_val.shape
+    dev = corr_val.device
+    if vox is None:
+        vox = torch.empty(b, n, levels * 27, dtype=torch.float32, device=dev)
+    if knn_sel is None:
+        knn_sel = torch.empty(b, n, KNN, 4, dtype=torch.float32, device=dev)
+    if moments is None:
+        moments = torch.zeros(b, MOMENTS, dtype=torch.float64, device=dev)
+    slots = torch.empty(b, n, KNN, dtype=torch.int32, device=dev) if want_slots else None
+    cube = torch.empty(b, n, k, levels, dtype=torch.int8, device=dev) if want_cube else None
+    _count(lib().pvraft_corr_lookup_fwd(_p(corr_val), _p(corr_idx, torch.int32), _p(xyz2p), _p(coords), b, n, k, levels,
+                                        float(base_scale), _p(vox), _p(knn_sel), _p(slots, torch.int32),
+                                        _p(moments, torch.float64), _p(cube, torch.int8), _stream()), 'corr_lookup')
+    return dict(vox=vox, knn_sel=knn_sel, moments=moments, knn_slot=slots, cube=cube)
+
+
+def linear(x, weight, bias=None, *, cin=None, w_ld=0, in_mode=IN_PLAIN, in_min=None, in_stats=None, in_gamma=None,
+           in_beta=None, in_count=0.0, in_act=ACT_NONE, in_slope=0.0, out_act=ACT_NONE, out=None, out_stats=None,
+           residual=None, cout=None):
+    """Fused [GN -> act ->] 1x1 conv [+bias] [-> ReLU] [+ residual] over x [B,N,cin] -> [B,N,cout]."""
+    b, n, c = x.shape
+    cin = c if cin is None else cin
+    cout = weight.shape[0] if cout is None else cout
+    if out is None:
+        out = torch.empty(b, n, cout, dtype=torch.float32, device=x.device)
+    a = _lib.LinearArgs(_p(x), _p(in_min), _p(in_stats, torch.float64), _p(in_gamma), _p(in_beta), float(in_count),
+                        in_mode, in_act, float(in_slope), _p(weight), int(w_ld), _p(bias), _p(residual), out_act,
+                        _p(out), _p(out_stats, torch.float64), b, n, cin, cout)
+    _count(lib().pvraft_linear_fwd(C.byref(a), _stream()), 'linear')
+    return out
+
+
+def gn_act(x, stats, gamma, beta, count, act=ACT_LRELU, slope=0.1, transpose_out=False):
+    b, n, c = x.shape
+    out = torch.empty((b, c, n) if transpose_out else (b, n, c), dtype=torch.float32, device=x.device)
+    _count(lib().pvraft_gn_act_fwd(_p(x), _p(stats, torch.float64), _p(gamma), _p(beta), float(count), act, float(slope),
+                                   b, n, c, int(transpose_out), _p(out), _stream()), 'gn_act')
+    return out
+
+
+def transpose(x):
+    """[B,R,C] -> [B,C,R] contiguous."""
+    b, r, c = x.shape
+    out = torch.empty(b, c, r, dtype=torch.float32, device=x.device)
+    _count(lib().pvraft_transpose_fwd(_p(x), b, r, c, _p(out), _stream()), 'transpose')
+    return out
+
+
+def corr_feature(args):
+    _count(lib().pvraft_corr_feature_fwd(C.byref(args), _stream()), 'corr_feature')
+
+
+def gru(args):
+    _count(lib().pvraft_gru_fwd(C.byref(args), _stream()), 'gru')
+
+
+def flow_out(args):
+    _count(lib().pvraft_flow_out_fwd(C.byref(args), _stream()), 'flow_out')
+
+
+def setconv_edge(fc1p, nbr, edge_feats, w_fc1, cin, stats, ymax=None, ymin=None):
+    b, n, c = fc1p.shape
+    if ymax is None:
+        ymax = torch.empty_like(fc1p)
+    if ymin is None:
+        ymin = torch.empty_like(fc1p)
+    _count(lib().pvraft_setconv_edge_fwd(_p(fc1p), _p(nbr, torch.int32), _p(edge_feats), _p(w_fc1), cin, b, n, c, _p(ymax),
+                                         _p(ymin), _p(stats, torch.float64), _stream()), 'setconv_edge')
+    return ymax, ymin
+
+
+def knn(xyz, query, k, mode=0, want_rel=False):
+    """-> int32 [B,S,k] local ids of the k nearest `xyz` points of every query (unordered)
+    [, rel [B,S,k,3] = xyz[idx] - query]."""
+    b, n, _ = xyz.shape
+    s = query.shape[1]
+    out = torch.empty(b, s, k, dtype=torch.int32, device=xyz.device)
+    rel = torch.empty(b, s, k, 3, dtype=torch.float32, device=xyz.device) if want_rel else None
+    _count(lib().pvraft_knn_fwd(_p(xyz), _p(query), b, n, s, k, mode, _p(out, torch.int32), _p(rel), _stream()), 'knn')
+    return (out, rel) if want_rel else out
+
+
+def device_info():
+    sm, smem = C.c_int(0), C.c_int(0)
+    check(lib().pvraft_device_info(C.byref(sm), C.byref(smem)), 'device_info')
+    return sm.value, smem.value

@@ -1,0 +1,100 @@
+"""RSF / RSF_refine -- drop-in mirrors of model/RAFTSceneFlow.py:10-50 and
+model/RAFTSceneFlowRefine.py:10-48: same constructor (`args.corr_levels/base_scales/truncate_k`),
+same submodule attribute names and state_dict keys, same `forward(p, num_iters)` contract.
+
+The loop body keeps every tensor point-major on the device, launches a fixed sequence of kernels
+per iteration with no host synchronisation, and fuses the RAFT glue (flow = coords2 - coords1,
+coords2 += delta, model/RAFTSceneFlow.py:41-46) into the first / last kernel of the iteration.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .corr import CorrBlock
+from .extractor import FlotEncoder
+from .refine import FlotRefine
+from .update import UpdateBlock
+
+
+def _require_inference(module):
+    if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
+        raise NotImplementedError(
+            'pvraft_b200: the backward kernels are not built yet -- run the forward under torch.no_grad() '
+            '(inference / evaluation).  Training support is the next row of DESIGN.md.')
+
+
+class _RaftBase(nn.Module):
+    def _encode(self, p):
+        xyz1, xyz2 = p[0], p[1]
+        if xyz1.dim() != 3 or xyz1.shape[-1] != 3 or xyz1.shape != xyz2.shape:
+            raise ValueError('expected p = [xyz1 [B,N,3], xyz2 [B,N,3]]')
+        xyz1 = xyz1.detach().contiguous().float()
+        xyz2 = xyz2.detach().contiguous().float()
+        fmap1, graph = self.feature_extractor(xyz1)                      # RAFTSceneFlow.py:25
+        fmap2, _ = self.feature_extractor(xyz2)                          # :26
+        self.corr_block.init_module(fmap1, fmap2, xyz2)                  # :29
+        # the reference rebuilds the same pc1 graph for the context encoder (:31); reuse it
+        fct1, graph_context = self.context_extractor(xyz1, graph=graph, point_major=True)
+        net = torch.tanh(fct1[..., :self.hidden_dim]).contiguous()       # :33-35 (point-major split)
+        inp = torch.relu(fct1[..., self.hidden_dim:]).contiguous()
+        return xyz1, xyz2, graph, graph_context, net, inp
+
+    def _iterate(self, xyz1, graph_context, net, inp, num_iters, keep_all):
+        b, n, _ = xyz1.shape
+        coords2 = xyz1.clone()
+        flow = torch.zeros_like(xyz1)
+        preds = []
+        me = self.update_block.motion_encoder
+        for _ in range(num_iters):
+            motion = torch.empty(b, n, 64, dtype=torch.float32, device=xyz1.device)
+
+            def attach(a, keep, flow=flow, motion=motion):
+                me.fill(a, flow)
+                a.motion = ops._p(motion)
+                keep.append(motion)
+
+            _, keep = self.corr_block.feature_point_major(coords2, motion_args=attach)   # :42 + update.py:83
+            new_flow = torch.empty_like(xyz1)
+            net, _ = self.update_block.forward_pm(net, inp, motion, graph_context, coords1=xyz1, coords2=coords2,
+                                                  coords2_out=coords2, flow_out=new_flow)   # :44-46
+            flow = new_flow
+            if keep_all:
+                preds.append(flow)
+        return flow, preds
+
+
+class RSF(_RaftBase):
+    def __init__(self, args):
+        super().__init__()
+        self.hidden_dim = 64
+        self.context_dim = 64
+        self.feature_extractor = FlotEncoder()
+        self.context_extractor = FlotEncoder()
+        self.corr_block = CorrBlock(num_levels=args.corr_levels, base_scale=args.base_scales,
+                                    resolution=3, truncate_k=args.truncate_k)
+        self.update_block = UpdateBlock(hidden_dim=self.hidden_dim)
+
+    def forward(self, p, num_iters=12):
+        _require_inference(self)
+        xyz1, _, _, graph_context, net, inp = self._encode(p)
+        _, preds = self._iterate(xyz1, graph_context, net, inp, num_iters, keep_all=True)
+        return preds
+
+
+class RSF_refine(_RaftBase):
+    def __init__(self, args):
+        super().__init__()
+        self.hidden_dim = 64
+        self.context_dim = 64
+        self.feature_extractor = FlotEncoder()
+        self.context_extractor = FlotEncoder()
+        self.corr_block = CorrBlock(num_levels=args.corr_levels, base_scale=args.base_scales,
+                                    resolution=3, truncate_k=args.truncate_k)
+        self.update_block = UpdateBlock(hidden_dim=self.hidden_dim)
+        self.refine_block = FlotRefine()
+
+    def forward(self, p, num_iters=12):
+        _require_inference(self)
+        xyz1, _, graph, graph_context, net, inp = self._encode(p)
+        flow, _ = self._iterate(xyz1, graph_context, net, inp, num_iters, keep_all=False)
+        return self.refine_block(flow, graph)                            # RAFTSceneFlowRefine.py:46

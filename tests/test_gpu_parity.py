@@ -1,0 +1,301 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors.
+
+Tolerances (SURVEY.md section 8c / BASELINE.md): indices bit-exact (sorted-set compare, exact-distance
+ties exempt); teacher-forced module outputs 1e-5 relative (max-abs / max-abs) in fp32; free-running
+flows looser because discrete decisions (voxel rounding, kNN) amplify 1-ulp differences.
+"""
+import types
+
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import pvraft_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope='module')
+def dev():
+    return torch.device('cuda:0')
+
+
+def state_to_dev(state, xyz2, dev):
+    return state.truncated_corr.to(dev), state.indices.to(torch.int32).to(dev), xyz2.to(dev)
+
+
+def block_with_state(state, xyz2, dev, levels=3, base_scale=0.25, k=None):
+    from pvraft_b200 import CorrBlock
+    cb = CorrBlock(num_levels=levels, base_scale=base_scale, truncate_k=k or state.truncated_corr.shape[-1]).to(dev)
+    cb.set_state(*state_to_dev(state, xyz2, dev))
+    return cb
+
+
+# ----------------------------------------------------------------------------------------------------
+# lookup kernel: indices, means, kNN selection, moments
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('b,n,k,box,levels,scale', [
+    (2, 256, 64, 3.0, 3, 0.25),      # dense cells
+    (1, 1024, 512, 10.0, 3, 0.25),   # sparse (reference-like)
+    (2, 512, 128, 2.0, 3, 0.25),     # very dense: nearly every candidate valid at the coarsest level
+    (1, 300, 32, 3.0, 2, 0.3),       # K = 32 (every candidate is a neighbour), non power-of-two scale, ragged N
+    (1, 256, 256, 1.5, 4, 0.125),    # 4 levels
+    (1, 2048, 1024, 4.0, 1, 0.5),    # K = 1024, single level
+])
+def test_lookup_against_oracle(dev, b, n, k, box, levels, scale):
+    from pvraft_b200 import ops
+    state, coords, xyz2 = O.synthetic_state(b, n, k, seed=n + k, box=box)
+    cb = block_with_state(state, xyz2, dev, levels, scale)
+    out = cb.lookup(coords.to(dev), want_slots=True, want_cube=True)
+    torch.cuda.synchronize()
+    # (1) cube index + validity of EVERY candidate, bit-exact (model/corr.py:52-62)
+    for lvl in range(levels):
+        cube, valid = O.voxel_cube_index(state, coords, scale * 2 ** lvl)
+        got = out['cube'][..., lvl].cpu()
+        assert torch.equal(got >= 0, valid), f'level {lvl}: validity differs'
+        assert torch.equal(torch.where(got >= 0, got, torch.zeros_like(got)).long(), cube), f'level {lvl}: cell differs'
+    # (2) voxel means: sequential ascending-k sums == the oracle's scatter_add order -> expect bit-exact
+    want = O.voxel_means(state, coords, levels, scale).transpose(1, 2)
+    got = out['vox'].cpu()
+    assert rel_err(got, want) < 1e-6
+    assert (got != want).float().mean() < 1e-3, 'voxel means are expected to be (almost always) bit-identical'
+    # (3) kNN slots: same SET as the oracle except at exact-distance ties of the 32nd neighbour
+    dist = O.knn_sqdist(state, coords)
+    want_slots = O.knn_select(state, coords).sort(-1).values
+    got_slots = out['knn_slot'].cpu().long().sort(-1).values
+    bad = (want_slots != got_slots).any(-1)
+    if bad.any():
+        kth = torch.gather(dist, 2, want_slots).max(-1).values
+        mine = torch.gather(dist, 2, got_slots).max(-1).values
+        assert torch.equal(kth[bad], mine[bad]), 'kNN sets differ beyond exact ties'
+    assert (got_slots[..., 1:] > got_slots[..., :-1]).all(), 'duplicate neighbour slots'
+    # (4) the gathered 4-vectors are exactly (corr, xyz - coords) of the selected slots
+    sl = out['knn_slot'].cpu().long()
+    want_sel = O.knn_gather(state, coords, sl).permute(0, 2, 3, 1)
+    assert torch.equal(out['knn_sel'].cpu(), want_sel)
+    # (5) moments of the 4-vectors in double precision
+    f = out['knn_sel'].cpu().double().reshape(b, -1, 4)
+    m = out['moments'].cpu()
+    assert torch.allclose(m[:, :4], f.sum(1), rtol=1e-12, atol=1e-9)
+    iu = torch.triu_indices(4, 4)
+    second = torch.einsum('bni,bnj->bij', f, f)[:, iu[0], iu[1]]
+    assert torch.allclose(m[:, 4:14], second, rtol=1e-12, atol=1e-9)
+    assert torch.equal(m[:, 14], torch.full((b,), float(n * 32), dtype=torch.float64))
+
+
+def test_lookup_duplicate_points_ties(dev):
+    """Exact-distance ties (duplicated xyz2 points): the kernel must still return 32 distinct slots whose
+    distances are the 32 smallest."""
+    state, coords, xyz2 = O.synthetic_state(1, 256, 64, seed=3, box=3.0)
+    xyz2[:, 1::2] = xyz2[:, 0::2]                       # every point duplicated
+    cand = torch.gather(xyz2.unsqueeze(1).expand(1, 256, 256, 3), 2, state.indices.unsqueeze(-1).expand(1, 256, 64, 3))
+    state = O.CorrState(state.truncated_corr, state.indices, cand.contiguous())
+    cb = block_with_state(state, xyz2, dev)
+    out = cb.lookup(coords.to(dev), want_slots=True)
+    dist = O.knn_sqdist(state, coords)
+    got = out['knn_slot'].cpu().long().sort(-1).values
+    assert (got[..., 1:] > got[..., :-1]).all()
+    kth = dist.sort(-1).values[..., 31]
+    assert torch.equal(torch.gather(dist, 2, got).max(-1).values, kth)
+    want = O.voxel_means(state, coords, 3, 0.25).transpose(1, 2)
+    assert rel_err(out['vox'].cpu(), want) < 1e-6
+
+
+def test_lookup_full_size_properties(dev):
+    """BASELINE size (N=8192, K=512, B=2): oracle on a random subsample of rows + global invariants."""
+    b, n, k = 2, 8192, 512
+    state, coords, xyz2 = O.synthetic_state(b, n, k, seed=1, box=10.0)
+    cb = block_with_state(state, xyz2, dev)
+    out = cb.lookup(coords.to(dev), want_slots=True)
+    torch.cuda.synchronize()
+    rows = torch.randperm(n, generator=torch.Generator().manual_seed(0))[:512]
+    sub = O.CorrState(state.truncated_corr[:, rows], state.indices[:, rows], state.truncate_xyz2[:, rows])
+    csub = coords[:, rows]
+    want = O.voxel_means(sub, csub, 3, 0.25).transpose(1, 2)
+    assert rel_err(out['vox'].cpu()[:, rows], want) < 1e-6
+    want_slots = O.knn_select(sub, csub).sort(-1).values
+    got_slots = out['knn_slot'].cpu().long()[:, rows].sort(-1).values
+    assert (want_slots != got_slots).any(-1).float().mean() < 1e-3
+    # invariant: permuting the candidate order of every row changes neither the kNN set nor (beyond
+    # rounding) the voxel means
+    perm = torch.randperm(k, generator=torch.Generator().manual_seed(1))
+    cb2 = block_with_state(O.CorrState(state.truncated_corr[..., perm], state.indices[..., perm], None), xyz2, dev)
+    out2 = cb2.lookup(coords.to(dev), want_slots=True)
+    assert rel_err(out2['vox'], out['vox']) < 1e-5
+    a = torch.gather(cb.corr_idx, 2, out['knn_slot'].long()).sort(-1).values
+    c = torch.gather(cb2.corr_idx, 2, out2['knn_slot'].long()).sort(-1).values
+    assert (a != c).any(-1).float().mean() < 1e-3
+
+
+# ----------------------------------------------------------------------------------------------------
+# truncation (top-K) and kNN graph
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('b,n,m,k', [(2, 64, 256, 64), (1, 128, 1024, 512), (1, 33, 700, 100), (1, 16, 8192, 512)])
+def test_corr_topk(dev, b, n, m, k):
+    from pvraft_b200 import ops
+    g = torch.Generator().manual_seed(m + k)
+    corr = torch.randn(b, n, m, generator=g)
+    corr[:, :, ::7] = corr[:, :, 3:4]            # plenty of exact ties
+    val, idx = ops.corr_topk(corr.to(dev), k)
+    top = torch.topk(corr, k, dim=2, sorted=True)
+    assert torch.equal(val.cpu(), top.values)                                   # values are unique as a multiset
+    assert torch.equal(torch.gather(corr, 2, idx.cpu().long()), top.values)     # indices point at them
+    s = idx.cpu().long().sort(-1).values
+    assert (s[..., 1:] > s[..., :-1]).all(), 'duplicate columns'
+
+
+@pytest.mark.parametrize('b,n', [(2, 256), (1, 1000), (1, 4096)])
+def test_knn_graph_matches_oracle(dev, b, n):
+    from pvraft_b200 import Graph
+    pc, _ = O.synthetic_clouds(b, n, seed=n)
+    g = Graph.construct_graph(pc.to(dev), 32)
+    want = O.construct_graph(pc, 32)
+    got = g.nbr.cpu().long().sort(-1).values
+    ref = (want.edges.reshape(b, n, 32) - (torch.arange(b) * n).view(b, 1, 1)).sort(-1).values
+    bad = (got != ref).any(-1)
+    # mismatches are only allowed at exact ties of the 32nd distance
+    if bad.any():
+        d = O.pairwise_sqdist_expanded(pc)
+        assert torch.equal(torch.gather(d, 2, got).max(-1).values[bad], torch.gather(d, 2, ref).max(-1).values[bad])
+    assert bad.float().mean() < 0.01
+    # edge features = neighbour - centre
+    rel = pc.unsqueeze(2).expand(b, n, n, 3).gather(1, g.nbr.cpu().long().unsqueeze(-1).expand(b, n, 32, 3)) if False else None
+    nb = g.nbr.cpu().long()
+    want_rel = torch.gather(pc.unsqueeze(1).expand(b, n, n, 3), 2, nb.unsqueeze(-1).expand(b, n, 32, 3)) - pc.unsqueeze(2)
+    assert torch.equal(g.edge_feats.cpu().reshape(b, n, 32, 3), want_rel)
+    assert torch.equal(g.edges.cpu(), (nb + (torch.arange(b) * n).view(b, 1, 1)).reshape(-1))
+
+
+def test_knn_point_golden(dev):
+    from pvraft_b200 import knn_point
+    arr, _ = load_golden('knn_point.npz')
+    idx = knn_point(16, arr['xyz'].to(dev), arr['query'].to(dev))
+    assert idx.dtype == torch.int64
+    assert torch.equal(idx.cpu().sort(-1).values.int(), arr['idx'])
+
+
+# ----------------------------------------------------------------------------------------------------
+# teacher-forced modules against the golden vectors of the unmodified reference
+# ----------------------------------------------------------------------------------------------------
+def golden_model(fixture, dev, refine):
+    from pvraft_b200 import RSF, RSF_refine
+    arr, W = load_golden(fixture)
+    b, n, k, levels, iters = [int(v) for v in arr['meta']]
+    args = types.SimpleNamespace(corr_levels=levels, base_scales=float(arr['base_scale']), truncate_k=k)
+    m = (RSF_refine if refine else RSF)(args)
+    m.load_state_dict(W, strict=True)
+    return arr, W, m.to(dev).eval()
+
+
+def install_golden_state(m, arr, dev):
+    """Teacher forcing: rebuild the candidate index from the golden truncate_xyz2 (exact coordinate match)."""
+    txyz, pc2 = arr['truncate_xyz2'], arr['pc2']
+    b, n, k, _ = txyz.shape
+    idx = torch.empty(b, n, k, dtype=torch.int64)
+    for bi in range(b):
+        eq = (txyz[bi].reshape(n * k, 1, 3) == pc2[bi].unsqueeze(0)).all(-1)
+        idx[bi] = eq.float().argmax(-1).reshape(n, k)
+    m.corr_block.set_state(arr['truncated_corr'].to(dev), idx.to(dev), pc2.to(dev))
+    assert torch.equal(m.corr_block.truncate_xyz2.cpu(), txyz)
+
+
+def golden_graph(arr, dev):
+    from pvraft_b200 import Graph
+    e = arr['graph_edges'].long()
+    b, n, k = e.shape
+    nbr = (e - (torch.arange(b) * n).view(b, 1, 1)).to(torch.int32)
+    rel = arr['graph_edge_feats'].reshape(b, n, k, 3)
+    return Graph(nbr.to(dev), rel.to(dev).contiguous(), k, [b * n, b * n])
+
+
+@pytest.mark.parametrize('fixture,refine', [('small_rsf_refine.npz', True), ('oddscale_rsf.npz', False)])
+def test_modules_teacher_forced_vs_reference(dev, fixture, refine):
+    arr, W, m = golden_model(fixture, dev, refine)
+    install_golden_state(m, arr, dev)
+    g = golden_graph(arr, dev)
+    iters = int(arr['meta'][4])
+    inp = torch.relu(arr['fct1'][:, 64:]).to(dev)
+    net = torch.tanh(arr['fct1'][:, :64]).to(dev)
+    with torch.no_grad():
+        for it in range(iters):
+            coords = arr[f'it{it}/coords'].to(dev)
+            corr = m.corr_block(coords)                                            # CorrBlock.__call__
+            assert rel_err(corr.cpu(), arr[f'it{it}/corr']) < TOL
+            vox = m.corr_block.get_voxel_feature(coords)
+            assert rel_err(vox.cpu(), arr[f'it{it}/voxel_feature']) < TOL
+            knn = m.corr_block.get_knn_feature(coords)
+            assert rel_err(knn.cpu(), arr[f'it{it}/knn_feature']) < 5e-5            # difference of two features
+            flow = (coords - arr['pc1'].to(dev))
+            gcorr = arr[f'it{it}/corr'].to(dev)
+            mot = m.update_block.motion_encoder(flow, gcorr)
+            assert rel_err(mot.cpu(), arr[f'it{it}/motion']) < TOL
+            net2, delta = m.update_block(net, inp, gcorr, flow, g)                 # UpdateBlock.forward
+            assert rel_err(net2.cpu(), arr[f'it{it}/net']) < TOL
+            assert rel_err(delta.cpu(), arr[f'it{it}/delta']) < 5e-5
+            net = arr[f'it{it}/net'].to(dev)
+
+
+def test_setconv_and_encoder_vs_oracle(dev):
+    from pvraft_b200 import FlotEncoder, Graph
+    arr, W = load_golden('small_rsf_refine.npz')
+    enc = FlotEncoder()
+    enc.load_state_dict({k[len('feature_extractor.'):]: v for k, v in W.items() if k.startswith('feature_extractor.')})
+    enc = enc.to(dev).eval()
+    g = golden_graph(arr, dev)
+    with torch.no_grad():
+        fmap, _ = enc(arr['pc1'].to(dev), graph=g)
+    assert fmap.shape == arr['fmap1'].shape
+    assert rel_err(fmap.cpu(), arr['fmap1']) < TOL
+    # single layers, every channel configuration of the model (3->32, 32->64, 64->128, 64->64)
+    og = O.Graph(arr['graph_edges'].reshape(-1).long(), arr['graph_edge_feats'], 32, (0, 0))
+    x = arr['pc1']
+    for name in ('feat_conv1', 'feat_conv2', 'feat_conv3'):
+        want = O.set_conv(W, 'feature_extractor.' + name, x, og)
+        with torch.no_grad():
+            got = getattr(enc, name)(x.to(dev), g)
+        assert rel_err(got.cpu(), want) < TOL
+        x = want
+
+
+# ----------------------------------------------------------------------------------------------------
+# end to end
+# ----------------------------------------------------------------------------------------------------
+def test_rsf_refine_free_running_small(dev):
+    arr, W, m = golden_model('small_rsf_refine.npz', dev, refine=True)
+    from pvraft_b200 import RSF
+    iters = int(arr['meta'][4])
+    p = [arr['pc1'].to(dev), arr['pc2'].to(dev)]
+    with torch.no_grad():
+        refined = m(p, iters)
+    assert refined.shape == arr['refined'].shape
+    scale = float(arr['refined'].abs().mean())
+    assert float((refined.cpu() - arr['refined']).abs().mean()) < 2e-3 * scale
+    # the non-refine model with the same weights returns the per-iteration list (RAFTSceneFlow.py:50)
+    args = types.SimpleNamespace(corr_levels=3, base_scales=0.25, truncate_k=int(arr['meta'][2]))
+    rsf = RSF(args)
+    rsf.load_state_dict(W, strict=False)
+    rsf = rsf.to(dev).eval()
+    with torch.no_grad():
+        flows = rsf(p, num_iters=iters)
+    assert isinstance(flows, list) and len(flows) == iters
+    for it in range(iters):
+        ref = arr[f'it{it}/flow']
+        assert float((flows[it].cpu() - ref).abs().mean()) < 2e-3 * float(ref.abs().mean())
+
+
+def test_rsf_default_init_medium(dev):
+    """N=1024, K=512, default seeded init (the same RNG stream as the reference's RSF(args))."""
+    from pvraft_b200 import RSF
+    arr, _ = load_golden('medium_rsf.npz')
+    b, n, k, levels, iters = [int(v) for v in arr['meta']]
+    args = types.SimpleNamespace(corr_levels=levels, base_scales=0.25, truncate_k=k)
+    torch.manual_seed(0)
+    m = RSF(args).to(dev).eval()
+    with torch.no_grad():
+        flows = m([arr['pc1'].to(dev), arr['pc2'].to(dev)], iters)
+    cs = arr['truncated_corr_checksum']
+    assert abs(float(m.corr_block.truncated_corr.double().sum()) - float(cs[0])) < 1e-5 * float(cs[1])
+    for it in range(iters):
+        ref = arr[f'it{it}/flow']
+        assert float((flows[it].cpu() - ref).abs().mean()) < 2e-3 * float(ref.abs().mean())

@@ -1,0 +1,144 @@
+"""CPU-only tests: the C-ABI library loads and exports what the header declares, the Python mirror
+matches the reference's module surface, the product path has no CPU fallback, and the multi-process
+sharding logic works over gloo."""
+import ctypes
+import os
+import re
+import socket
+import types
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    from pvraft_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'pvraft_b200.h')).read()
+    declared = set(re.findall(r'PVRAFT_API\s+[\w\s\*]+?\b(pvraft_\w+)\s*\(', hdr))
+    assert len(declared) >= 15
+    handle = ctypes.CDLL(_lib.LIB_PATH) if os.path.exists(_lib.LIB_PATH) else _lib.lib()
+    for name in declared:
+        assert hasattr(handle, name), f'{name} is declared in the header but not exported'
+    assert declared == set(_lib.EXPORTS), 'ctypes binding and header disagree'
+    lib = _lib.lib()
+    assert lib.pvraft_version() == 100
+    for which, struct in enumerate([_lib.LinearArgs, _lib.CorrFeatArgs, _lib.GruArgs, _lib.FlowOutArgs]):
+        assert lib.pvraft_sizeof(which) == ctypes.sizeof(struct), f'struct {struct.__name__} layout drifted'
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    from pvraft_b200 import _lib
+    lib = _lib.lib()
+    rc = lib.pvraft_corr_lookup_fwd(None, None, None, None, 1, 64, 64, 3, 0.25, None, None, None, None, None, None)
+    assert rc == -1 and b'null' in lib.pvraft_last_error_string()
+    rc = lib.pvraft_corr_lookup_fwd(8, 8, 8, 8, 1, 64, 96, 3, 0.25, 8, 8, None, None, None, None)
+    assert rc == -2 and b'truncate_k=96' in lib.pvraft_last_error_string()
+    rc = lib.pvraft_knn_fwd(8, 8, 1, 16, 16, 33, 0, 8, None, None)
+    assert rc == -2
+    with pytest.raises(_lib.PvraftError):
+        _lib.check(rc, 'knn')
+
+
+def test_module_surface_matches_reference_state_dict():
+    from pvraft_b200 import RSF, RSF_refine
+    arr, W = load_golden('small_rsf_refine.npz')
+    args = types.SimpleNamespace(corr_levels=3, base_scales=0.25, truncate_k=64)
+    m = RSF_refine(args)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(W.keys())            # same keys, same order as the reference
+    for k in W:
+        assert tuple(sd[k].shape) == tuple(W[k].shape), k
+    m.load_state_dict(W, strict=True)
+    rsf = RSF(args)
+    missing = rsf.load_state_dict(W, strict=False)       # tools/engine_refine.py:110 style
+    assert not missing.missing_keys and all(k.startswith('refine_block.') for k in missing.unexpected_keys)
+    for attr in ('feature_extractor', 'context_extractor', 'corr_block', 'update_block', 'refine_block'):
+        assert hasattr(m, attr)
+    assert len(sd) == 124 and sum(p.numel() for p in rsf.parameters()) == 192034
+
+
+def test_reference_import_paths():
+    from model.RAFTSceneFlow import RSF
+    from model.RAFTSceneFlowRefine import RSF_refine
+    from model.corr import CorrBlock
+    from model.update import UpdateBlock
+    from model.pointconv import knn_point
+    from model.flot.gconv import SetConv
+    from model.flot.graph import Graph
+    import pvraft_b200
+    assert RSF is pvraft_b200.RSF and RSF_refine is pvraft_b200.RSF_refine
+    assert CorrBlock is pvraft_b200.CorrBlock and UpdateBlock is pvraft_b200.UpdateBlock
+    assert callable(knn_point) and SetConv is pvraft_b200.SetConv and Graph is pvraft_b200.Graph
+
+
+def test_no_cpu_fallback():
+    from oracle import pvraft_oracle as O
+    from pvraft_b200 import RSF, _lib
+    args = types.SimpleNamespace(corr_levels=3, base_scales=0.25, truncate_k=32)
+    m = RSF(args).eval()
+    pc, pc2 = O.synthetic_clouds(1, 64)
+    with torch.no_grad(), pytest.raises(_lib.PvraftError):
+        m([pc, pc2], 1)
+    with pytest.raises(NotImplementedError):             # training needs the (unbuilt) backward kernels
+        m([pc, pc2], 1)
+
+
+def test_product_never_imports_the_oracle():
+    pat = re.compile(r'^\s*(from|import)\s+oracle|import_module\(.oracle|oracle/', re.M)
+    for top in ('pvraft_b200', 'model'):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith('.py'):
+                    assert not pat.search(open(os.path.join(dirpath, f)).read()), f'{f} reaches into oracle/'
+
+
+def test_shard_range_covers_batch():
+    from pvraft_b200.dist import shard_range
+    for total in (1, 2, 7, 8, 16, 17):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from pvraft_b200 import dist as D
+    r, w, _ = D.init_from_env(backend='gloo')
+    g = torch.Generator().manual_seed(0)
+    xyz1 = torch.rand(5, 16, 3, generator=g)
+    xyz2 = torch.rand(5, 16, 3, generator=g)
+    mine = D.shard_batch([xyz1, xyz2], r, w)
+    local = mine[0] * 2.0 + mine[1]                    # stands in for the per-sample forward
+    full = D.gather_batch(local)
+    ok = torch.equal(full, xyz1 * 2.0 + xyz2)
+    t = D.max_over_ranks(1.0 + r)
+    s = D.sum_over_ranks(float(mine[0].shape[0]))
+    D.barrier()
+    out[rank] = (ok, t, s)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_shard_gather_and_timing():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for r in range(world):
+        ok, t, s = out[r]
+        assert ok and t == 2.0 and s == 5.0
