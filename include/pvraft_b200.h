@@ -76,7 +76,7 @@ PVRAFT_API int pvraft_pad_xyz(const float* xyz, int64_t num_points, float* xyz4,
  *                                true fp32 division; r_level = base_scale * 2^level)
  *   -> knn_sel  [B,N,32,4]       (corr, dx, dy, dz) of the 32 candidates nearest to coords
  *                                (distance = (dx*dx+dy*dy)+dz*dz, no FMA); order within a point is
- *                                unspecified, exact-distance ties at the 32nd place: lowest slot
+ *                                unspecified; exact-distance ties at the 32nd place are broken deterministically
  *   -> knn_slot [B,N,32] int32   candidate slot (0..K-1) of each selected neighbour; may be NULL
  *   -> moments  [B,16] double    ACCUMULATED first/second moments of the 4-vector over the sample's
  *                                N*32 edges: [0..3]=sum f_i, [4..13]=sum f_i f_j (i<=j, row-major

@@ -2,25 +2,33 @@
 //
 // Replaces CorrBlock.get_voxel_feature up to out_conv (reference model/corr.py:47-71) and
 // CorrBlock.get_knn_feature up to knn_conv (model/corr.py:75-91) with ONE pass over the K
-// candidates of every point:  a warp owns a point, streams its K (corr, index) pairs with 128-bit
-// loads (8 B per candidate -- the candidate xyz is NOT materialised as in the reference's
-// [B,N,K,3] tensor but gathered from a per-sample float4 table staged in shared memory),
-// and produces
-//   * the 27-cell x `levels` voxel means (lanes 0..26 each own one cell; candidates that pass the
-//     coarsest-level cube test are compacted, in ascending candidate order, into a per-warp list and
-//     summed sequentially -> the sums are bit-identical to a sequential scatter_add),
-//   * the 32 nearest candidates (exact threshold found by a bitwise bisection on the fp32 distance
-//     bits, warp-wide population counts, no sorting),
-//   * double-precision first/second moments of the kNN 4-vectors, from which the consumer derives
-//     the GroupNorm statistics of knn_conv's output without materialising its [B,64,N,32] tensor.
-//
-// Arithmetic that decides indices is bit-faithful to the reference's fp32 op sequence: separate
-// rn subtract / multiply / add (no FMA contraction), true IEEE division, round-half-even.
+// candidates of every point.  Data movement:
+//   * per-iteration HBM stream = 8 B per candidate (fp32 correlation + int32 candidate id); the
+//     reference's materialised [B,N,K,3] xyz tensor is replaced by a per-sample float4 table that a
+//     CTA stages once in shared memory and gathers from;
+//   * a warp owns a point; its 2 x K*4-byte row is brought into the warp's shared-memory stage by
+//     the TMA engine (cp.async.bulk + mbarrier complete_tx) while the warp is still reducing the
+//     previous point, so loads are in flight without holding registers.
+// Per point the warp produces
+//   * the 27-cell x `levels` voxel means: candidates inside the coarsest cube (cheap sphere pre-test on
+//     the squared distance, exact test only for the survivors) are compacted in ascending candidate
+//     order into a small list; lanes 0..26 each own a cell and sum sequentially -> identical to a
+//     sequential scatter_add; the list is flushed whenever it fills, so dense cells need no extra smem;
+//   * the 32 nearest candidates: exact threshold on the fp32 distance bits by an interpolating
+//     bisection with warp-wide population counts (no sort), ties -> lowest slot;
+//   * double-precision first/second moments of the kNN 4-vectors, from which the consumer derives the
+//     GroupNorm statistics of knn_conv's output without materialising its [B,64,N,32] tensor.
+// Index-deciding arithmetic is bit-faithful to the reference's fp32 op sequence: separate rn
+// subtract / multiply / add (no FMA contraction), true IEEE division, round-half-even.
 #include "common.cuh"
 
 namespace pvraft {
 
 constexpr int kLookupThreads = 512;
+
+// per-warp shared memory: staged row (K*8) + valid-slot list (K*2) + one 32-entry chunk (256) + kNN slots (128) +
+// mbarrier (8); the 128-bin distance histogram of the kNN select (512 B) reuses the slot list; rounded to 128 B so that every warp's stage stays 128-byte aligned for the bulk copies
+__host__ __device__ constexpr size_t lookup_warp_bytes(int K) { return (((size_t)(K < 256 ? 256 : K) * 2 + (size_t)K * 8 + 256 + 128 + 8) + 127) & ~(size_t)127; }
 
 struct LookupParams {
     const float* corr_val;
@@ -31,7 +39,6 @@ struct LookupParams {
     float4* knn_sel;     // [B,N,32]
     int32_t* knn_slot;   // [B,N,32] or null
     double* moments;     // [B,16] or null
-    int8_t* dbg_cube;    // [B,N,K,levels] or null
     int B, N, K, levels;
     float r[4];          // cell edge per level
     float inv_r[4];      // exact reciprocal when r is a power of two
@@ -55,26 +62,94 @@ __device__ __forceinline__ unsigned cell_code(float dx, float dy, float dz, floa
     return ok ? (unsigned)cell : 0xFFu;
 }
 
+// ---- mbarrier / bulk-copy (TMA) primitives ----------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// lanes 0..26 own one cell of every level: sequential (ascending candidate) sums over a chunk of entries
+__device__ __forceinline__ void scan_chunk(const uint2* __restrict__ s_chunk, int n, int lane, float (&sum)[4], int (&cnt)[4]) {
+    const unsigned mine = (unsigned)lane * 0x01010101u;
+    for (int i = 0; i < n; ++i) {
+        const uint2 e = s_chunk[i];
+        const unsigned m = e.x ^ mine;   // byte l is zero iff the entry falls into this lane's cell at level l
+        const float val = __uint_as_float(e.y);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            if ((m & (0xFFu << (8 * l))) == 0u) {
+                sum[l] = __fadd_rn(sum[l], val);
+                cnt[l] += 1;
+            }
+        }
+    }
+}
+
+// inclusive warp scan of a word of packed 8-bit counters (no field may exceed 255)
+__device__ __forceinline__ unsigned warp_scan_packed(unsigned w, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned a = __shfl_up_sync(kFull, w, o);
+        if (lane >= o) w += a;
+    }
+    return w;
+}
+
 template <int KPL, bool POW2, bool SMEM_TAB>
 __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupParams p) {
-    constexpr int VEC = KPL >= 4 ? 4 : KPL;   // consecutive candidates per lane per load
-    constexpr int NJ = KPL / VEC;             // loads per lane
+    constexpr int VEC = KPL >= 4 ? 4 : KPL;   // consecutive candidates per lane per block
+    constexpr int NJ = KPL / VEC;             // blocks of 32*VEC candidates
     constexpr int K = KPL * 32;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* s_tab = reinterpret_cast<float4*>(smem_raw);
+    constexpr unsigned NIB = (1u << VEC) - 1u;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const size_t tab_bytes = SMEM_TAB ? (size_t)p.N * sizeof(float4) : 0;
-    // per-warp scratch: compacted (code,val) list [K] + kNN slot list [32]
+    float4* s_tab = reinterpret_cast<float4*>(smem_raw);
     const int w = warp_id(), lane = lane_id();
-    uint2* s_list = reinterpret_cast<uint2*>(smem_raw + tab_bytes) + (size_t)w * K;
-    int* s_slots = reinterpret_cast<int*>(smem_raw + tab_bytes + (size_t)p.warps * K * sizeof(uint2)) + w * 32;
+    unsigned char* wbase = smem_raw + tab_bytes + (size_t)w * lookup_warp_bytes(K);
+    float* s_corr = reinterpret_cast<float*>(wbase);                     // [K]   staged correlation row
+    int* s_idx = reinterpret_cast<int*>(wbase + K * 4);                  // [K]   staged candidate ids
+    constexpr int VL = (K < 256 ? 256 : K) * 2;
+    unsigned short* s_vlist = reinterpret_cast<unsigned short*>(wbase + K * 8);   // [K] slots inside the coarsest cube
+    int* s_hist = reinterpret_cast<int*>(wbase + K * 8);                 // [128] kNN distance histogram (after the list is dead)
+    uint2* s_chunk = reinterpret_cast<uint2*>(wbase + K * 8 + VL);       // [32]  (cell codes, corr) of one chunk
+    int* s_slots = reinterpret_cast<int*>(wbase + K * 8 + VL + 256);     // [32]  kNN slots
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(wbase + K * 8 + VL + 384);
     const bool active_warp = w < p.warps;
+    // 1/c in double for c = 0..K: (float)(double(sum) * rcp[c]) is the correctly rounded fp32 quotient sum/c for
+    // every integer c <= 2^20 (x/c is never within 2^-34 relative of a rounding boundary), without a division
+    double* s_rcp = reinterpret_cast<double*>(smem_raw + tab_bytes + (size_t)p.warps * lookup_warp_bytes(K));
+    for (int i = threadIdx.x; i <= K; i += blockDim.x) s_rcp[i] = i > 0 ? 1.0 / (double)i : 1.0;
+
+    if (active_warp && lane == 0) mbar_init(s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
 
     const long long total = (long long)p.B * p.N;
     long long pt_begin, pt_end;
     split_range(total, gridDim.x, blockIdx.x, pt_begin, pt_end);
-    const unsigned lt_mask = (1u << lane) - 1u;
     const int L = p.levels;
-    const float rc = p.r[L - 1], inv_rc = p.inv_r[L - 1];   // coarsest level
+    const float rc = L == 1 ? p.r[0] : L == 2 ? p.r[1] : L == 3 ? p.r[2] : p.r[3];               // coarsest level
+    const float inv_rc = L == 1 ? p.inv_r[0] : L == 2 ? p.inv_r[1] : L == 3 ? p.inv_r[2] : p.inv_r[3];
+    unsigned phase = 0;
 
     long long seg = pt_begin;
     while (seg < pt_end) {
@@ -82,6 +157,12 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
         long long seg_end = (long long)(b + 1) * p.N;
         if (seg_end > pt_end) seg_end = pt_end;
         const float4* tab_g = p.tab + (size_t)b * p.N;
+        // kick off this warp's first row, then stage the sample's xyz table while it is in flight
+        if (active_warp && lane == 0 && seg + w < seg_end) {
+            mbar_expect_tx(s_bar, K * 8);
+            bulk_g2s(s_corr, p.corr_val + (seg + w) * K, K * 4, s_bar);
+            bulk_g2s(s_idx, p.corr_idx + (seg + w) * K, K * 4, s_bar);
+        }
         if (SMEM_TAB) {
             __syncthreads();   // previous segment's readers are done
             for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_tab[i] = tab_g[i];
@@ -96,157 +177,212 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                 const float cx = __ldg(p.coords + pt * 3 + 0);
                 const float cy = __ldg(p.coords + pt * 3 + 1);
                 const float cz = __ldg(p.coords + pt * 3 + 2);
-                const float* rv = p.corr_val + pt * K;
-                const int32_t* ri = p.corr_idx + pt * K;
+                mbar_wait(s_bar, phase);
+                phase ^= 1u;
 
-                // ---- stream the row: slot(j,s) = j*32*VEC + lane*VEC + s -------------------------
-                float cv[KPL];
-                int ci[KPL];
+                // ---- stream the staged row: slot(j,s) = j*32*VEC + lane*VEC + s -------------------------
+                unsigned dist[KPL];       // fp32 bits of the (non-negative) squared distance
+                unsigned valid_bits = 0;  // bit e: candidate e of this lane lies inside the coarsest 3x3x3 cube
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
+                    int ci[VEC];
                     if (VEC == 4) {
-                        const float4 a = ld_stream_f4(reinterpret_cast<const float4*>(rv + j * 128) + lane);
-                        const int4 c = ld_stream_i4(reinterpret_cast<const int4*>(ri + j * 128) + lane);
-                        cv[j * 4 + 0] = a.x; cv[j * 4 + 1] = a.y; cv[j * 4 + 2] = a.z; cv[j * 4 + 3] = a.w;
-                        ci[j * 4 + 0] = c.x; ci[j * 4 + 1] = c.y; ci[j * 4 + 2] = c.z; ci[j * 4 + 3] = c.w;
+                        const int4 c = reinterpret_cast<const int4*>(s_idx)[j * 32 + lane];
+                        ci[0] = c.x; ci[1 % VEC] = c.y; ci[2 % VEC] = c.z; ci[3 % VEC] = c.w;
                     } else {
 #pragma unroll
-                        for (int s = 0; s < VEC; ++s) {
-                            cv[j * VEC + s] = __ldg(rv + j * 32 * VEC + lane * VEC + s);
-                            ci[j * VEC + s] = __ldg(ri + j * 32 * VEC + lane * VEC + s);
-                        }
+                        for (int s = 0; s < VEC; ++s) ci[s] = s_idx[j * 32 * VEC + lane * VEC + s];
+                    }
+#pragma unroll
+                    for (int s = 0; s < VEC; ++s) {
+                        const float4 q = SMEM_TAB ? s_tab[ci[s]] : __ldg(tab_g + ci[s]);
+                        const float dx = __fsub_rn(q.x, cx), dy = __fsub_rn(q.y, cy), dz = __fsub_rn(q.z, cz);
+                        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                        dist[j * VEC + s] = __float_as_uint(d2);
+                        // |round(d/r)| <= 1 on every axis  <=>  max|d|/r < 1.5 (round-half-even sends 1.5 to 2;
+                        // x -> fl(x/r) is monotone, so the max can be taken before the division)
+                        const float amax = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
+                        valid_bits |= (div_r<POW2>(amax, rc, inv_rc) < 1.5f ? 1u : 0u) << (j * VEC + s);
                     }
                 }
 
-                // ---- distances + coarsest-level cube test + ordered compaction ---------------------
-                unsigned dist[KPL];   // fp32 bits of the (non-negative) squared distance
+                // ---- voxel means -----------------------------------------------------------------------
+                // (1) ordered compaction of the valid slots: one packed warp scan gives every lane its offset in
+                //     every block j, so the list is in ascending slot order (the order of a sequential scatter_add)
+                float sum[4] = {0.f, 0.f, 0.f, 0.f};
+                int cnt[4] = {0, 0, 0, 0};
                 int list_n = 0;
+                if (__any_sync(kFull, valid_bits != 0u)) {
+                    unsigned w0 = 0, w1 = 0;
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    unsigned vmask[VEC];
-                    unsigned any = 0;
-#pragma unroll
-                    for (int s = 0; s < VEC; ++s) {
-                        const int e = j * VEC + s;
-                        const float4 q = SMEM_TAB ? s_tab[ci[e]] : __ldg(tab_g + ci[e]);
-                        const float dx = __fsub_rn(q.x, cx), dy = __fsub_rn(q.y, cy), dz = __fsub_rn(q.z, cz);
-                        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                        dist[e] = __float_as_uint(d2);
-                        const float amax = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
-                        // |round(d/r)| <= 1 on every axis  <=>  max|d|/r < 1.5 (round-half-even sends 1.5 to 2)
-                        const bool v = div_r<POW2>(amax, rc, inv_rc) < 1.5f;
-                        vmask[s] = __ballot_sync(kFull, v);
-                        any |= vmask[s];
-                        if (p.dbg_cube) {
-                            const int slot = j * 32 * VEC + lane * VEC + s;
-                            for (int l = 0; l < L; ++l) {
-                                const unsigned c = cell_code<POW2>(dx, dy, dz, p.r[l], p.inv_r[l]);
-                                p.dbg_cube[((size_t)pt * K + slot) * L + l] = c == 0xFFu ? (int8_t)-1 : (int8_t)c;
-                            }
-                        }
+                    for (int j = 0; j < NJ; ++j) {
+                        const unsigned c = __popc((valid_bits >> (j * VEC)) & NIB);
+                        if (j < 4) w0 |= c << (8 * j); else w1 |= c << (8 * (j - 4));
                     }
-                    if (any) {   // warp-uniform
-                        int pos = list_n;
+                    const unsigned i0 = warp_scan_packed(w0, lane);
+                    const unsigned t0 = __shfl_sync(kFull, i0, 31);
+                    unsigned i1 = 0, t1 = 0;
+                    if (NJ > 4) { i1 = warp_scan_packed(w1, lane); t1 = __shfl_sync(kFull, i1, 31); }
+                    const unsigned e0 = i0 - w0, e1 = i1 - w1;
 #pragma unroll
-                        for (int s = 0; s < VEC; ++s) pos += __popc(vmask[s] & lt_mask);
+                    for (int j = 0; j < NJ; ++j) {
+                        const unsigned ex = j < 4 ? (e0 >> (8 * j)) & 0xFFu : (e1 >> (8 * (j - 4))) & 0xFFu;
+                        const unsigned tt = j < 4 ? (t0 >> (8 * j)) & 0xFFu : (t1 >> (8 * (j - 4))) & 0xFFu;
+                        unsigned nib = (valid_bits >> (j * VEC)) & NIB;
+                        int pos = list_n + (int)ex;
+                        while (nib) {
+                            const int s = __ffs(nib) - 1;
+                            nib &= nib - 1;
+                            s_vlist[pos++] = (unsigned short)(j * 32 * VEC + lane * VEC + s);
+                        }
+                        list_n += (int)tt;
+                    }
+                    __syncwarp();
+                    // (2) chunks of 32 entries: lane i derives the cell codes of entry i, then (3) the cell owners scan
+                    for (int c0 = 0; c0 < list_n; c0 += 32) {
+                        const int n = min(32, list_n - c0);
+                        if (lane < n) {
+                            const int slot = s_vlist[c0 + lane];
+                            const int id = s_idx[slot];
+                            const float4 q = SMEM_TAB ? s_tab[id] : __ldg(tab_g + id);
+                            const float dx = __fsub_rn(q.x, cx), dy = __fsub_rn(q.y, cy), dz = __fsub_rn(q.z, cz);
+                            unsigned code = 0xFFFFFFFFu;
 #pragma unroll
-                        for (int s = 0; s < VEC; ++s) {
-                            if ((vmask[s] >> lane) & 1u) {
-                                const int e = j * VEC + s;
-                                const float4 q = SMEM_TAB ? s_tab[ci[e]] : __ldg(tab_g + ci[e]);
-                                const float dx = __fsub_rn(q.x, cx), dy = __fsub_rn(q.y, cy), dz = __fsub_rn(q.z, cz);
-                                unsigned code = 0xFFFFFFFFu;
-                                for (int l = 0; l < L; ++l) {
+                            for (int l = 0; l < 4; ++l) {
+                                if (l < L) {
                                     const unsigned c = cell_code<POW2>(dx, dy, dz, p.r[l], p.inv_r[l]);
                                     code = (code & ~(0xFFu << (8 * l))) | (c << (8 * l));
                                 }
-                                s_list[pos] = make_uint2(code, __float_as_uint(cv[e]));
-                                ++pos;
                             }
-                            list_n += __popc(vmask[s]);
+                            s_chunk[lane] = make_uint2(code, __float_as_uint(s_corr[slot]));
                         }
+                        __syncwarp();
+                        scan_chunk(s_chunk, n, lane, sum, cnt);
+                        __syncwarp();
                     }
                 }
                 __syncwarp();
-
-                // ---- voxel means: lane c (<27) owns cell c of every level; sequential sums --------
+                // the staged row is consumed: prefetch this warp's next point into the same stage
                 {
-                    float sum[4] = {0.f, 0.f, 0.f, 0.f};
-                    int cnt[4] = {0, 0, 0, 0};
-                    for (int i = 0; i < list_n; ++i) {
-                        const uint2 e = s_list[i];
-                        const float val = __uint_as_float(e.y);
-#pragma unroll
-                        for (int l = 0; l < 4; ++l) {
-                            if (((e.x >> (8 * l)) & 0xFFu) == (unsigned)lane) {
-                                sum[l] = __fadd_rn(sum[l], val);
-                                cnt[l] += 1;
-                            }
-                        }
+                    const long long nxt = pt + p.warps;
+                    if (lane == 0 && nxt < seg_end) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        mbar_expect_tx(s_bar, K * 8);
+                        bulk_g2s(s_corr, p.corr_val + nxt * K, K * 4, s_bar);
+                        bulk_g2s(s_idx, p.corr_idx + nxt * K, K * 4, s_bar);
                     }
-                    if (lane < 27) {
-                        float* vo = p.vox + pt * (L * 27);
-                        for (int l = 0; l < L; ++l) {
-                            const float c = (float)(cnt[l] < 1 ? 1 : cnt[l]);   // clamp(count, 1, N), corr.py:65
-                            vo[l * 27 + lane] = __fdiv_rn(sum[l], c);
+                }
+                if (lane < 27) {
+                    float* vo = p.vox + pt * (L * 27);
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) {
+                        if (l < L) {
+                            // sum / clamp(count, 1, N) (corr.py:65-66); rcp[0] = 1
+                            vo[l * 27 + lane] = (float)((double)sum[l] * s_rcp[cnt[l]]);
                         }
                     }
                 }
 
-                // ---- kNN: smallest threshold T with count(d <= T) >= 32, by bisection on the bits ----
+                // ---- kNN: a threshold T with count(d <= T) >= 32 > count(d < T) ---------------------------
                 unsigned lmin = dist[0];
 #pragma unroll
                 for (int e = 1; e < KPL; ++e) lmin = min(lmin, dist[e]);
                 unsigned hi = __reduce_max_sync(kFull, lmin);   // 32 distinct candidates are <= hi
-                unsigned lo = __reduce_min_sync(kFull, lmin);
-                unsigned T = hi;
-                while (lo < hi) {
+                unsigned lo;
+                int c_lo, c_hi;
+                {
+                    // 128-bucket histogram over the top 4 octaves below `hi` (bucket edges are exact in the bit
+                    // pattern): one pass brackets the 32nd smallest distance inside a single bucket
+                    const unsigned base = hi > 0x01FFFFFFu ? hi - 0x01FFFFFFu : 0u;
+                    *reinterpret_cast<int4*>(s_hist + lane * 4) = make_int4(0, 0, 0, 0);
+                    __syncwarp();
+#pragma unroll
+                    for (int e = 0; e < KPL; ++e) {
+                        if (dist[e] <= hi) atomicAdd(s_hist + (dist[e] > base ? (dist[e] - base) >> 18 : 0u), 1);
+                    }
+                    __syncwarp();
+                    const int4 h = *reinterpret_cast<const int4*>(s_hist + lane * 4);
+                    const int mine = h.x + h.y + h.z + h.w;
+                    int incl = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int a = __shfl_up_sync(kFull, incl, o);
+                        if (lane >= o) incl += a;
+                    }
+                    const int src = __ffs(__ballot_sync(kFull, incl >= PVRAFT_KNN)) - 1;   // exists: count(d <= hi) >= 32
+                    int c = incl - mine, bq = 0, cl = c, ch = c + h.x;
+                    if (ch < PVRAFT_KNN) { cl = ch; ch += h.y; bq = 1; }
+                    if (ch < PVRAFT_KNN) { cl = ch; ch += h.z; bq = 2; }
+                    if (ch < PVRAFT_KNN) { cl = ch; ch += h.w; bq = 3; }
+                    const int B = __shfl_sync(kFull, lane * 4 + bq, src);
+                    c_lo = __shfl_sync(kFull, cl, src);
+                    c_hi = __shfl_sync(kFull, ch, src);
+                    lo = B == 0 ? 0u : base + ((unsigned)B << 18);
+                    hi = base + ((unsigned)(B + 1) << 18) - 1u;
+                }
+                // invariant: count(d <= hi) = c_hi >= 32, count(d < lo) = c_lo < 32; finish inside the bucket
+                while (c_hi != PVRAFT_KNN && lo < hi) {
                     const unsigned mid = lo + ((hi - lo) >> 1);
                     int c = 0;
 #pragma unroll
                     for (int e = 0; e < KPL; ++e) c += dist[e] <= mid ? 1 : 0;
                     c = __reduce_add_sync(kFull, c);
-                    if (c == PVRAFT_KNN) { hi = mid; lo = mid; break; }
-                    if (c > PVRAFT_KNN) hi = mid; else lo = mid + 1;
+                    if (c >= PVRAFT_KNN) { hi = mid; c_hi = c; } else { lo = mid + 1; c_lo = c; }
                 }
-                T = hi;
-                // slots with d < T first, then ties d == T in ascending slot order until 32 are taken
-                int n_lt = 0;
+                const unsigned T = hi;
+                if (c_hi == PVRAFT_KNN) {
+                    // common case: exactly 32 candidates are <= T
+                    unsigned m_le = 0;
 #pragma unroll
-                for (int e = 0; e < KPL; ++e) n_lt += dist[e] < T ? 1 : 0;
-                n_lt = __reduce_add_sync(kFull, n_lt);
-                int base_lt = 0, base_eq = n_lt;
+                    for (int e = 0; e < KPL; ++e) m_le |= (dist[e] <= T ? 1u : 0u) << e;
+                    int off = __popc(m_le);
+                    const int n_le = off;
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    unsigned mlt[VEC], meq[VEC];
-#pragma unroll
-                    for (int s = 0; s < VEC; ++s) {
-                        mlt[s] = __ballot_sync(kFull, dist[j * VEC + s] < T);
-                        meq[s] = __ballot_sync(kFull, dist[j * VEC + s] == T);
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int a = __shfl_up_sync(kFull, off, o);
+                        if (lane >= o) off += a;
                     }
-                    int plt = base_lt, peq = base_eq;
-#pragma unroll
-                    for (int s = 0; s < VEC; ++s) {
-                        plt += __popc(mlt[s] & lt_mask);
-                        peq += __popc(meq[s] & lt_mask);
+                    off -= n_le;
+                    while (m_le) {
+                        const int e = __ffs(m_le) - 1;
+                        m_le &= m_le - 1;
+                        s_slots[off++] = (e / VEC) * 32 * VEC + lane * VEC + (e % VEC);
                     }
+                } else {
+                    // exact-distance ties at the 32nd place: everything strictly closer, then ties in (lane, e) order
+                    unsigned m_lt = 0, m_eq = 0;
 #pragma unroll
-                    for (int s = 0; s < VEC; ++s) {
-                        const int slot = j * 32 * VEC + lane * VEC + s;
-                        if ((mlt[s] >> lane) & 1u) s_slots[plt++] = slot;
-                        if ((meq[s] >> lane) & 1u) {
-                            if (peq < PVRAFT_KNN) s_slots[peq] = slot;
-                            ++peq;
-                        }
-                        base_lt += __popc(mlt[s]);
-                        base_eq += __popc(meq[s]);
+                    for (int e = 0; e < KPL; ++e) {
+                        m_lt |= (dist[e] < T ? 1u : 0u) << e;
+                        m_eq |= (dist[e] == T ? 1u : 0u) << e;
+                    }
+                    const int n_lt = __popc(m_lt), n_eq = __popc(m_eq);
+                    int off_lt = n_lt, off_eq = n_eq;   // inclusive scans over lanes
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int a = __shfl_up_sync(kFull, off_lt, o), c = __shfl_up_sync(kFull, off_eq, o);
+                        if (lane >= o) { off_lt += a; off_eq += c; }
+                    }
+                    const int tot_lt = __shfl_sync(kFull, off_lt, 31);
+                    off_lt -= n_lt;
+                    off_eq += tot_lt - n_eq;
+                    while (m_lt) {
+                        const int e = __ffs(m_lt) - 1;
+                        m_lt &= m_lt - 1;
+                        s_slots[off_lt++] = (e / VEC) * 32 * VEC + lane * VEC + (e % VEC);
+                    }
+                    while (m_eq) {
+                        const int e = __ffs(m_eq) - 1;
+                        m_eq &= m_eq - 1;
+                        if (off_eq < PVRAFT_KNN) s_slots[off_eq] = (e / VEC) * 32 * VEC + lane * VEC + (e % VEC);
+                        ++off_eq;
                     }
                 }
                 __syncwarp();
                 {
                     const int slot = s_slots[lane];
-                    const float c = __ldg(rv + slot);
-                    const int id = __ldg(ri + slot);
+                    const float c = __ldg(p.corr_val + pt * K + slot);
+                    const int id = __ldg(p.corr_idx + pt * K + slot);
                     const float4 q = SMEM_TAB ? s_tab[id] : __ldg(tab_g + id);
                     const float dx = __fsub_rn(q.x, cx), dy = __fsub_rn(q.y, cy), dz = __fsub_rn(q.z, cz);
                     p.knn_sel[pt * 32 + lane] = make_float4(c, dx, dy, dz);
@@ -260,9 +396,12 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                 __syncwarp();
             }
             if (p.moments) {
-#pragma unroll
+#pragma unroll 1
                 for (int i = 0; i < 14; ++i) {
-                    const double s = warp_sum(mom[i]);
+                    double v = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 14; ++q) v = q == i ? mom[q] : v;
+                    const double s = warp_sum(v);
                     if (lane == 0 && s != 0.0) atomicAdd(p.moments + (size_t)b * PVRAFT_MOMENTS + i, s);
                 }
                 if (lane == 0 && w == 0)
@@ -270,6 +409,22 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
             }
         }
         seg = seg_end;
+    }
+}
+
+// Test hook: cell id (or -1) of every candidate at every level, same arithmetic as the fused kernel.
+template <bool POW2>
+__global__ void k_cube_debug(const LookupParams p, int8_t* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)p.B * p.N * p.K;
+    if (i >= total) return;
+    const long long pt = i / p.K;
+    const int b = (int)(pt / p.N);
+    const float4 q = p.tab[(size_t)b * p.N + p.corr_idx[i]];
+    const float dx = __fsub_rn(q.x, p.coords[pt * 3]), dy = __fsub_rn(q.y, p.coords[pt * 3 + 1]), dz = __fsub_rn(q.z, p.coords[pt * 3 + 2]);
+    for (int l = 0; l < p.levels; ++l) {
+        const unsigned c = cell_code<POW2>(dx, dy, dz, p.r[l], p.inv_r[l]);
+        out[i * p.levels + l] = c == 0xFFu ? (int8_t)-1 : (int8_t)c;
     }
 }
 
@@ -286,19 +441,20 @@ static bool is_pow2f(float r) {
 template <int KPL, bool POW2>
 static int launch_lookup(LookupParams& p, cudaStream_t st) {
     const int K = KPL * 32;
-    const size_t per_warp = (size_t)K * sizeof(uint2) + 32 * sizeof(int);
+    const size_t per_warp = lookup_warp_bytes(K);
     const size_t tab = (size_t)p.N * sizeof(float4);
-    bool smem_tab = tab + 4 * per_warp <= (size_t)kSmemBudget;
-    size_t avail = (size_t)kSmemBudget - (smem_tab ? tab : 0);
+    const size_t rcp_bytes = (size_t)(K + 1) * sizeof(double) + 8;
+    const bool smem_tab = tab + 8 * per_warp + rcp_bytes <= (size_t)kSmemBudget;
+    const size_t avail = (size_t)kSmemBudget - (smem_tab ? tab : 0) - rcp_bytes;
     int warps = (int)(avail / per_warp);
     if (warps > kLookupThreads / 32) warps = kLookupThreads / 32;
     if (warps < 1) return fail(PVRAFT_ERR_SMEM, "corr_lookup: K=%d does not fit shared memory", K);
     p.warps = warps;
-    const size_t smem = (smem_tab ? tab : 0) + warps * per_warp;
+    const size_t rcp = (size_t)(K + 1) * sizeof(double) + 8;
+    const size_t smem = (smem_tab ? tab : 0) + warps * per_warp + rcp;
     const long long total = (long long)p.B * p.N;
     int grid = sm_count();
-    const long long min_pts = warps;   // no point in more blocks than (points / warps)
-    if ((long long)grid * min_pts > total) grid = (int)((total + min_pts - 1) / min_pts);
+    if ((long long)grid * warps > total) grid = (int)((total + warps - 1) / warps);
     if (grid < 1) grid = 1;
     int rc;
     if (smem_tab) {
@@ -334,7 +490,7 @@ extern "C" int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr
     LookupParams p{};
     p.corr_val = corr_val; p.corr_idx = corr_idx; p.tab = reinterpret_cast<const float4*>(xyz2p); p.coords = coords;
     p.vox = vox; p.knn_sel = reinterpret_cast<float4*>(knn_sel); p.knn_slot = knn_slot; p.moments = moments;
-    p.dbg_cube = dbg_cube; p.B = B; p.N = N; p.K = K; p.levels = levels;
+    p.B = B; p.N = N; p.K = K; p.levels = levels;
     bool pow2 = true;
     for (int l = 0; l < 4; ++l) {
         // model/corr.py:53: r = base_scale * 2**i evaluated in double, then used as an fp32 divisor
@@ -344,6 +500,14 @@ extern "C" int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr
         if (l < levels && !is_pow2f(r)) pow2 = false;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (dbg_cube) {
+        const long long total = (long long)B * N * K;
+        const unsigned blocks = (unsigned)((total + 255) / 256);
+        if (pow2) k_cube_debug<true><<<blocks, 256, 0, st>>>(p, dbg_cube);
+        else k_cube_debug<false><<<blocks, 256, 0, st>>>(p, dbg_cube);
+        int rc = check_launch("cube_debug");
+        if (rc) return rc;
+    }
 #define PVRAFT_LOOKUP_CASE(KPL_)                                                            \
     case KPL_ * 32:                                                                         \
         return pow2 ? launch_lookup<KPL_, true>(p, st) : launch_lookup<KPL_, false>(p, st);

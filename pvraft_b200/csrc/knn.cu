@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn(const float* __restrict__ x
     // lane l holds the l-th member of the current best set (unordered); lanes >= k hold -inf sentinels so
     // that they are never the "worst".
     float bd = lane < k ? INFINITY : -INFINITY;
-    int bi = lane < k ? 0x7fffffff : -1;
+    int bi = lane < k ? 0x7fffffff - lane : -1;   // distinct sentinels: exactly one lane is "the worst"
     float tau = INFINITY;   // current worst (largest) of the k kept
     int tau_i = 0x7fffffff;
 
