@@ -63,14 +63,20 @@ PVRAFT_API int pvraft_device_info(int* sm_count, int* smem_optin_bytes);
  * --------------------------------------------------------------------------------------------- */
 PVRAFT_API int pvraft_corr_topk_fwd(const float* corr, int B, int N, int M, int K, float* val, int32_t* idx, void* stream);
 
-/* xyz [B,N,3] -> [B,N,4] (w = 0): the float4 gather table used by pvraft_corr_lookup_fwd. */
-PVRAFT_API int pvraft_pad_xyz(const float* xyz, int64_t num_points, float* xyz4, void* stream);
+/* ------------------------------------------------------------------------------------------------
+ * Bank-aware arrangement of the truncated state, once per forward (no reference counterpart: the order of
+ * the K candidates inside a row carries no meaning in model/corr.py beyond fp summation order).
+ * Every row of (val, idx) [rows, K] is permuted so that the 32 candidates the lookup kernel gathers with
+ * one instruction fall into (nearly) distinct shared-memory banks.  Out of place; deterministic.
+ * --------------------------------------------------------------------------------------------- */
+PVRAFT_API int pvraft_corr_reorder(const float* val_in, const int32_t* idx_in, int64_t rows, int K, float* val_out,
+                                   int32_t* idx_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Point-voxel correlation lookup (index + reduce part), one fused pass over the K candidates of
  * every point.  Replaces CorrBlock.get_voxel_feature up to (not incl.) out_conv, model/corr.py:47-71,
  * and CorrBlock.get_knn_feature up to (not incl.) knn_conv, model/corr.py:75-91.
- *   corr_val [B,N,K] f32, corr_idx [B,N,K] int32 (rows of xyz2), xyz2p [B,N,4], coords [B,N,3]
+ *   corr_val [B,N,K] f32, corr_idx [B,N,K] int32 (rows of xyz2), xyz2 [B,N,3], coords [B,N,3]
  *   -> vox      [B,N,levels*27]  channel = level*27 + cell; mean corr of the candidates whose
  *                                round((xyz-coords)/r_level) lies in {-1,0,1}^3  (round-half-even,
  *                                true fp32 division; r_level = base_scale * 2^level)
@@ -84,7 +90,7 @@ PVRAFT_API int pvraft_pad_xyz(const float* xyz, int64_t num_points, float* xyz4,
  *   -> dbg_cube [B,N,K,levels] int8  cell id or -1 of every candidate (test hook; NULL in production)
  * K in {32,64,128,256,512,1024}; 1 <= levels <= 4; knn fixed at 32.
  * --------------------------------------------------------------------------------------------- */
-PVRAFT_API int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr_idx, const float* xyz2p, const float* coords,
+PVRAFT_API int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr_idx, const float* xyz2, const float* coords,
                            int B, int N, int K, int levels, float base_scale, float* vox, float* knn_sel,
                            int32_t* knn_slot, double* moments, int8_t* dbg_cube, void* stream);
 

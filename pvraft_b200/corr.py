@@ -5,8 +5,10 @@ state_dict keys and call surface (`init_module`, `__call__(coords)`, `get_voxel_
 State layout differs from the reference on purpose: instead of the materialised
 `truncate_xyz2 [B,N,K,3]` (12 B/candidate) the block keeps the candidate INDEX (int32) next to the
 correlation value -- 8 B per candidate per iteration is the whole HBM stream of the lookup kernel;
-xyz is gathered from a 16 B/point table staged in shared memory.  `truncated_corr` and
-`truncate_xyz2` stay available as attributes/properties for API parity.
+xyz is gathered from a 12 B/point table staged in shared memory, and the K candidates of a row are
+stored in a bank-aware order (their order carries no meaning in the reference beyond fp summation
+order).  `truncated_corr` (sorted, as in the reference) and `truncate_xyz2` stay available as
+properties for API parity.
 """
 import torch
 import torch.nn as nn
@@ -43,9 +45,9 @@ class CorrBlock(nn.Module):
             nn.PReLU(),
         )
         self.knn_out = nn.Conv1d(64, 64, 1)
-        self.truncated_corr = None
-        self.corr_idx = None
-        self.xyz2p = None
+        self.corr_val = None     # [B,N,K] f32 correlation of the kept candidates (bank-aware order, see ops.corr_reorder)
+        self.corr_idx = None     # [B,N,K] int32 candidate ids (rows of xyz2), same order
+        self._xyz2 = None
 
     # ------------------------------------------------------------------------------------------
     @staticmethod
@@ -63,16 +65,20 @@ class CorrBlock(nn.Module):
         if n_p < self.truncate_k:
             raise ValueError(f'truncate_k={self.truncate_k} exceeds the number of points {n_p}')
         corr = self.calculate_corr(fmap1.detach().float(), fmap2.detach().float()).contiguous()
-        self.truncated_corr, self.corr_idx = ops.corr_topk(corr, self.truncate_k)
+        val, idx = ops.corr_topk(corr, self.truncate_k)
+        self.corr_val, self.corr_idx = ops.corr_reorder(val, idx)
         self._xyz2 = xyz2.detach().contiguous().float()
-        self.xyz2p = ops.pad_xyz(self._xyz2)
 
     def set_state(self, truncated_corr, corr_idx, xyz2):
         """Install an externally built state (tests / benchmarks): corr [B,N,K] f32, idx [B,N,K] int."""
-        self.truncated_corr = truncated_corr.contiguous().float()
-        self.corr_idx = corr_idx.contiguous().to(torch.int32)
+        self.corr_val, self.corr_idx = ops.corr_reorder(truncated_corr.contiguous().float(),
+                                                        corr_idx.contiguous().to(torch.int32))
         self._xyz2 = xyz2.contiguous().float()
-        self.xyz2p = ops.pad_xyz(self._xyz2)
+
+    @property
+    def truncated_corr(self):
+        """[B,N,K] correlation values sorted descending, as the reference keeps them (model/corr.py:38)."""
+        return None if self.corr_val is None else torch.sort(self.corr_val, dim=2, descending=True).values
 
     @property
     def truncate_xyz2(self):
@@ -83,14 +89,14 @@ class CorrBlock(nn.Module):
 
     @property
     def ones_matrix(self):
-        return torch.ones_like(self.truncated_corr)
+        return torch.ones_like(self.corr_val)
 
     # ------------------------------------------------------------------------------------------
     def lookup(self, coords, **kw):
         """Index + reduce part of the lookup (pvraft_corr_lookup_fwd) -> dict(vox, knn_sel, moments, ...)."""
-        if self.truncated_corr is None:
+        if self.corr_val is None:
             raise RuntimeError('CorrBlock.init_module must run before the lookup')
-        return ops.corr_lookup(self.truncated_corr, self.corr_idx, self.xyz2p, coords.detach().contiguous().float(),
+        return ops.corr_lookup(self.corr_val, self.corr_idx, self._xyz2, coords.detach().contiguous().float(),
                                self.num_levels, self.base_scale, **kw)
 
     def feature_args(self, lk, y1, y1_stats, b, n):

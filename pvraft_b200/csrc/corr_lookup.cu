@@ -4,8 +4,9 @@
 // CorrBlock.get_knn_feature up to knn_conv (model/corr.py:75-91) with ONE pass over the K
 // candidates of every point.  Data movement:
 //   * per-iteration HBM stream = 8 B per candidate (fp32 correlation + int32 candidate id); the
-//     reference's materialised [B,N,K,3] xyz tensor is replaced by a per-sample float4 table that a
-//     CTA stages once in shared memory and gathers from;
+//     reference's materialised [B,N,K,3] xyz tensor is replaced by a per-sample x/y/z table (3 x N floats)
+//     that a CTA stages once in shared memory and gathers from with 32-bit loads; pvraft_corr_reorder
+//     arranges every row once per forward so that the 32 lanes of a gather hit (nearly) distinct banks;
 //   * a warp owns a point; its 2 x K*4-byte row is brought into the warp's shared-memory stage by
 //     the TMA engine (cp.async.bulk + mbarrier complete_tx) while the warp is still reducing the
 //     previous point, so loads are in flight without holding registers.
@@ -24,16 +25,16 @@
 
 namespace pvraft {
 
-constexpr int kLookupThreads = 512;
+constexpr int kLookupThreads = 640;   // 20 warps: bounded by registers (<= 102/thread) and by shared memory
 
 // per-warp shared memory: staged row (K*8) + valid-slot list (K*2) + one 32-entry chunk (256) + kNN slots (128) +
 // mbarrier (8); the 128-bin distance histogram of the kNN select (512 B) reuses the slot list; rounded to 128 B so that every warp's stage stays 128-byte aligned for the bulk copies
-__host__ __device__ constexpr size_t lookup_warp_bytes(int K) { return (((size_t)(K < 256 ? 256 : K) * 2 + (size_t)K * 8 + 256 + 128 + 8) + 127) & ~(size_t)127; }
+__host__ __device__ constexpr size_t lookup_warp_bytes(int K) { return (((size_t)(K < 256 ? 256 : K) * 2 + (size_t)K * 8 + 256 + 128 + 16) + 127) & ~(size_t)127; }
 
 struct LookupParams {
     const float* corr_val;
     const int32_t* corr_idx;
-    const float4* tab;   // [B,N] (x,y,z,0)
+    const float* xyz2;   // [B,N,3]
     const float* coords; // [B,N,3]
     float* vox;          // [B,N,levels*27]
     float4* knn_sel;     // [B,N,32]
@@ -62,6 +63,15 @@ __device__ __forceinline__ unsigned cell_code(float dx, float dy, float dz, floa
     return ok ? (unsigned)cell : 0xFFu;
 }
 
+// xyz of candidate `id`: from the staged table (3 conflict-light 32-bit loads) or from global memory
+template <bool SMEM_TAB>
+__device__ __forceinline__ float3 gather_xyz(const float* __restrict__ s_tab, int n, const float* __restrict__ xyz_g, int id) {
+    // AoS [N][3]: word 3*id + c lives in bank (3*id + c) % 32, a bijection of id % 32 -> lanes with distinct
+    // id % 32 (what pvraft_corr_reorder arranges) never collide
+    if (SMEM_TAB) return make_float3(s_tab[3 * id], s_tab[3 * id + 1], s_tab[3 * id + 2]);
+    return make_float3(__ldg(xyz_g + 3 * (size_t)id), __ldg(xyz_g + 3 * (size_t)id + 1), __ldg(xyz_g + 3 * (size_t)id + 2));
+}
+
 // ---- mbarrier / bulk-copy (TMA) primitives ----------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
@@ -85,6 +95,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// bring a K-float row into L2 (64 B per lane per step); it is read sparsely (valid + kNN slots) afterwards
+__device__ __forceinline__ void prefetch_row(const float* row, int K, int lane) {
+    for (int o = lane * 16; o < K; o += 32 * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
 }
 
 // lanes 0..26 own one cell of every level: sequential (ascending candidate) sums over a chunk of entries
@@ -121,25 +136,24 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
     constexpr int K = KPL * 32;
     constexpr unsigned NIB = (1u << VEC) - 1u;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const size_t tab_bytes = SMEM_TAB ? (size_t)p.N * sizeof(float4) : 0;
-    float4* s_tab = reinterpret_cast<float4*>(smem_raw);
+    const size_t tab_bytes = SMEM_TAB ? (((size_t)p.N * 12 + 127) & ~(size_t)127) : 0;
+    float* s_tab = reinterpret_cast<float*>(smem_raw);   // [N][3], a verbatim copy of the sample's xyz2
     const int w = warp_id(), lane = lane_id();
     unsigned char* wbase = smem_raw + tab_bytes + (size_t)w * lookup_warp_bytes(K);
-    float* s_corr = reinterpret_cast<float*>(wbase);                     // [K]   staged correlation row
-    int* s_idx = reinterpret_cast<int*>(wbase + K * 4);                  // [K]   staged candidate ids
+    int* s_stage = reinterpret_cast<int*>(wbase);                        // [2][K] double-buffered candidate-id rows
     constexpr int VL = (K < 256 ? 256 : K) * 2;
     unsigned short* s_vlist = reinterpret_cast<unsigned short*>(wbase + K * 8);   // [K] slots inside the coarsest cube
     int* s_hist = reinterpret_cast<int*>(wbase + K * 8);                 // [128] kNN distance histogram (after the list is dead)
     uint2* s_chunk = reinterpret_cast<uint2*>(wbase + K * 8 + VL);       // [32]  (cell codes, corr) of one chunk
     int* s_slots = reinterpret_cast<int*>(wbase + K * 8 + VL + 256);     // [32]  kNN slots
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(wbase + K * 8 + VL + 384);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(wbase + K * 8 + VL + 384);   // [2]
     const bool active_warp = w < p.warps;
     // 1/c in double for c = 0..K: (float)(double(sum) * rcp[c]) is the correctly rounded fp32 quotient sum/c for
     // every integer c <= 2^20 (x/c is never within 2^-34 relative of a rounding boundary), without a division
     double* s_rcp = reinterpret_cast<double*>(smem_raw + tab_bytes + (size_t)p.warps * lookup_warp_bytes(K));
     for (int i = threadIdx.x; i <= K; i += blockDim.x) s_rcp[i] = i > 0 ? 1.0 / (double)i : 1.0;
 
-    if (active_warp && lane == 0) mbar_init(s_bar, 1);
+    if (active_warp && lane == 0) { mbar_init(s_bar, 1); mbar_init(s_bar + 1, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
@@ -149,23 +163,25 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
     const int L = p.levels;
     const float rc = L == 1 ? p.r[0] : L == 2 ? p.r[1] : L == 3 ? p.r[2] : p.r[3];               // coarsest level
     const float inv_rc = L == 1 ? p.inv_r[0] : L == 2 ? p.inv_r[1] : L == 3 ? p.inv_r[2] : p.inv_r[3];
-    unsigned phase = 0;
+    unsigned phase0 = 0, phase1 = 0;
 
     long long seg = pt_begin;
     while (seg < pt_end) {
         const int b = (int)(seg / p.N);
         long long seg_end = (long long)(b + 1) * p.N;
         if (seg_end > pt_end) seg_end = pt_end;
-        const float4* tab_g = p.tab + (size_t)b * p.N;
+        const float* tab_g = p.xyz2 + (size_t)b * p.N * 3;
         // kick off this warp's first row, then stage the sample's xyz table while it is in flight
-        if (active_warp && lane == 0 && seg + w < seg_end) {
-            mbar_expect_tx(s_bar, K * 8);
-            bulk_g2s(s_corr, p.corr_val + (seg + w) * K, K * 4, s_bar);
-            bulk_g2s(s_idx, p.corr_idx + (seg + w) * K, K * 4, s_bar);
+        if (active_warp && seg + w < seg_end) {
+            if (lane == 0) {
+                mbar_expect_tx(s_bar, K * 4);
+                bulk_g2s(s_stage, p.corr_idx + (seg + w) * K, K * 4, s_bar);
+            }
+            prefetch_row(p.corr_val + (seg + w) * K, K, lane);
         }
         if (SMEM_TAB) {
             __syncthreads();   // previous segment's readers are done
-            for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_tab[i] = tab_g[i];
+            for (int i = threadIdx.x; i < p.N * 3; i += blockDim.x) s_tab[i] = __ldg(tab_g + i);
             __syncthreads();
         }
         double mom[14];
@@ -177,8 +193,21 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                 const float cx = __ldg(p.coords + pt * 3 + 0);
                 const float cy = __ldg(p.coords + pt * 3 + 1);
                 const float cz = __ldg(p.coords + pt * 3 + 2);
-                mbar_wait(s_bar, phase);
-                phase ^= 1u;
+                const int cur = (int)(((pt - seg) / p.warps) & 1);
+                const int* s_idx = s_stage + cur * K;
+                {   // the other stage is free (its point is finished): start the next row now, a whole point ahead
+                    const long long nxt = pt + p.warps;
+                    if (nxt < seg_end) {
+                        if (lane == 0) {
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            mbar_expect_tx(s_bar + (cur ^ 1), K * 4);
+                            bulk_g2s(s_stage + (cur ^ 1) * K, p.corr_idx + nxt * K, K * 4, s_bar + (cur ^ 1));
+                        }
+                        prefetch_row(p.corr_val + nxt * K, K, lane);   // correlation row -> L2; read sparsely below
+                    }
+                }
+                if (cur == 0) { mbar_wait(s_bar, phase0); phase0 ^= 1u; } else { mbar_wait(s_bar + 1, phase1); phase1 ^= 1u; }
+                const float* rv = p.corr_val + pt * K;
 
                 // ---- stream the staged row: slot(j,s) = j*32*VEC + lane*VEC + s -------------------------
                 unsigned dist[KPL];       // fp32 bits of the (non-negative) squared distance
@@ -195,7 +224,7 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                     }
 #pragma unroll
                     for (int s = 0; s < VEC; ++s) {
-                        const float4 q = SMEM_TAB ? s_tab[ci[s]] : __ldg(tab_g + ci[s]);
+                        const float3 q = gather_xyz<SMEM_TAB>(s_tab, p.N, tab_g, ci[s]);
                         const float dx = __fsub_rn(q.x, cx), dy = __fsub_rn(q.y, cy), dz = __fsub_rn(q.z, cz);
                         const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
                         dist[j * VEC + s] = __float_as_uint(d2);
@@ -244,7 +273,7 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                         if (lane < n) {
                             const int slot = s_vlist[c0 + lane];
                             const int id = s_idx[slot];
-                            const float4 q = SMEM_TAB ? s_tab[id] : __ldg(tab_g + id);
+                            const float3 q = gather_xyz<SMEM_TAB>(s_tab, p.N, tab_g, id);
                             const float dx = __fsub_rn(q.x, cx), dy = __fsub_rn(q.y, cy), dz = __fsub_rn(q.z, cz);
                             unsigned code = 0xFFFFFFFFu;
 #pragma unroll
@@ -254,7 +283,7 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                                     code = (code & ~(0xFFu << (8 * l))) | (c << (8 * l));
                                 }
                             }
-                            s_chunk[lane] = make_uint2(code, __float_as_uint(s_corr[slot]));
+                            s_chunk[lane] = make_uint2(code, __float_as_uint(__ldg(rv + slot)));
                         }
                         __syncwarp();
                         scan_chunk(s_chunk, n, lane, sum, cnt);
@@ -262,16 +291,6 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                     }
                 }
                 __syncwarp();
-                // the staged row is consumed: prefetch this warp's next point into the same stage
-                {
-                    const long long nxt = pt + p.warps;
-                    if (lane == 0 && nxt < seg_end) {
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        mbar_expect_tx(s_bar, K * 8);
-                        bulk_g2s(s_corr, p.corr_val + nxt * K, K * 4, s_bar);
-                        bulk_g2s(s_idx, p.corr_idx + nxt * K, K * 4, s_bar);
-                    }
-                }
                 if (lane < 27) {
                     float* vo = p.vox + pt * (L * 27);
 #pragma unroll
@@ -381,9 +400,9 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                 __syncwarp();
                 {
                     const int slot = s_slots[lane];
-                    const float c = __ldg(p.corr_val + pt * K + slot);
-                    const int id = __ldg(p.corr_idx + pt * K + slot);
-                    const float4 q = SMEM_TAB ? s_tab[id] : __ldg(tab_g + id);
+                    const float c = __ldg(rv + slot);
+                    const int id = s_idx[slot];
+                    const float3 q = gather_xyz<SMEM_TAB>(s_tab, p.N, tab_g, id);
                     const float dx = __fsub_rn(q.x, cx), dy = __fsub_rn(q.y, cy), dz = __fsub_rn(q.z, cz);
                     p.knn_sel[pt * 32 + lane] = make_float4(c, dx, dy, dz);
                     if (p.knn_slot) p.knn_slot[pt * 32 + lane] = slot;
@@ -420,7 +439,8 @@ __global__ void k_cube_debug(const LookupParams p, int8_t* __restrict__ out) {
     if (i >= total) return;
     const long long pt = i / p.K;
     const int b = (int)(pt / p.N);
-    const float4 q = p.tab[(size_t)b * p.N + p.corr_idx[i]];
+    const float* q3 = p.xyz2 + ((size_t)b * p.N + p.corr_idx[i]) * 3;
+    const float3 q = make_float3(q3[0], q3[1], q3[2]);
     const float dx = __fsub_rn(q.x, p.coords[pt * 3]), dy = __fsub_rn(q.y, p.coords[pt * 3 + 1]), dz = __fsub_rn(q.z, p.coords[pt * 3 + 2]);
     for (int l = 0; l < p.levels; ++l) {
         const unsigned c = cell_code<POW2>(dx, dy, dz, p.r[l], p.inv_r[l]);
@@ -428,9 +448,54 @@ __global__ void k_cube_debug(const LookupParams p, int8_t* __restrict__ out) {
     }
 }
 
-__global__ void k_pad_xyz(const float* __restrict__ xyz, long long n, float4* __restrict__ out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = make_float4(xyz[i * 3], xyz[i * 3 + 1], xyz[i * 3 + 2], 0.f);
+// Bank-aware arrangement of one row's candidates (once per forward).  The lookup gathers x/y/z of 32
+// candidates per instruction: slots {j*32*VEC + lane*VEC + s} for a fixed (j,s).  A stable counting sort by
+// (id mod 32), dealt round-robin over the KPL (j,s) groups, leaves every group with (nearly) one candidate per
+// shared-memory bank.  One warp per row; deterministic (ranks come from warp match, not from atomics).
+template <int KPL>
+__global__ void __launch_bounds__(256) k_corr_reorder(const float* __restrict__ val_in, const int32_t* __restrict__ idx_in,
+                                                       long long rows, float* __restrict__ val_out, int32_t* __restrict__ idx_out) {
+    constexpr int VEC = KPL >= 4 ? 4 : KPL;
+    constexpr int K = KPL * 32;
+    __shared__ int s_cur[8][32];
+    const int lane = lane_id(), w = warp_id();
+    const long long row = (long long)blockIdx.x * 8 + w;
+    if (row >= rows) return;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    float v[KPL];
+    int id[KPL];
+    s_cur[w][lane] = 0;
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < KPL; ++e) {
+        v[e] = __ldg(val_in + row * K + e * 32 + lane);
+        id[e] = __ldg(idx_in + row * K + e * 32 + lane);
+        atomicAdd(&s_cur[w][id[e] & 31], 1);   // counts only: their value does not depend on the order of the adds
+    }
+    __syncwarp();
+    const int mycount = s_cur[w][lane];   // lane r: number of candidates with id % 32 == r
+    __syncwarp();
+    int start = mycount;   // exclusive scan over residues
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(kFull, start, o);
+        if (lane >= o) start += a;
+    }
+    s_cur[w][lane] = start - mycount;
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < KPL; ++e) {
+        const int r = id[e] & 31;
+        const unsigned m = __match_any_sync(kFull, r);
+        const int pos = s_cur[w][r] + __popc(m & lt_mask);
+        __syncwarp();
+        if (lane == __ffs(m) - 1) s_cur[w][r] += __popc(m);
+        __syncwarp();
+        const int g = pos % KPL, ln = pos / KPL;
+        const int slot = (g / VEC) * 32 * VEC + ln * VEC + (g % VEC);
+        val_out[row * K + slot] = v[e];
+        idx_out[row * K + slot] = id[e];
+    }
 }
 
 static bool is_pow2f(float r) {
@@ -442,7 +507,7 @@ template <int KPL, bool POW2>
 static int launch_lookup(LookupParams& p, cudaStream_t st) {
     const int K = KPL * 32;
     const size_t per_warp = lookup_warp_bytes(K);
-    const size_t tab = (size_t)p.N * sizeof(float4);
+    const size_t tab = (((size_t)p.N * 12 + 127) & ~(size_t)127);
     const size_t rcp_bytes = (size_t)(K + 1) * sizeof(double) + 8;
     const bool smem_tab = tab + 8 * per_warp + rcp_bytes <= (size_t)kSmemBudget;
     const size_t avail = (size_t)kSmemBudget - (smem_tab ? tab : 0) - rcp_bytes;
@@ -473,22 +538,34 @@ static int launch_lookup(LookupParams& p, cudaStream_t st) {
 
 using namespace pvraft;
 
-extern "C" int pvraft_pad_xyz(const float* xyz, int64_t n, float* xyz4, void* stream) {
-    if (!xyz || !xyz4 || n <= 0) return fail(PVRAFT_ERR_BAD_ARG, "pad_xyz: bad argument");
-    k_pad_xyz<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(xyz, n, reinterpret_cast<float4*>(xyz4));
-    return check_launch("pad_xyz");
+extern "C" int pvraft_corr_reorder(const float* val_in, const int32_t* idx_in, int64_t rows, int K, float* val_out,
+                                   int32_t* idx_out, void* stream) {
+    if (!val_in || !idx_in || !val_out || !idx_out || rows <= 0) return fail(PVRAFT_ERR_BAD_ARG, "corr_reorder: bad argument");
+    if (val_in == val_out || idx_in == idx_out) return fail(PVRAFT_ERR_BAD_ARG, "corr_reorder: in-place operation is not supported");
+    const unsigned blocks = (unsigned)((rows + 7) / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (K) {
+        case 32: k_corr_reorder<1><<<blocks, 256, 0, st>>>(val_in, idx_in, rows, val_out, idx_out); break;
+        case 64: k_corr_reorder<2><<<blocks, 256, 0, st>>>(val_in, idx_in, rows, val_out, idx_out); break;
+        case 128: k_corr_reorder<4><<<blocks, 256, 0, st>>>(val_in, idx_in, rows, val_out, idx_out); break;
+        case 256: k_corr_reorder<8><<<blocks, 256, 0, st>>>(val_in, idx_in, rows, val_out, idx_out); break;
+        case 512: k_corr_reorder<16><<<blocks, 256, 0, st>>>(val_in, idx_in, rows, val_out, idx_out); break;
+        case 1024: k_corr_reorder<32><<<blocks, 256, 0, st>>>(val_in, idx_in, rows, val_out, idx_out); break;
+        default: return fail(PVRAFT_ERR_UNSUPPORTED, "corr_reorder: truncate_k=%d (supported: 32,64,128,256,512,1024)", K);
+    }
+    return check_launch("corr_reorder");
 }
 
-extern "C" int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr_idx, const float* xyz2p,
+extern "C" int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr_idx, const float* xyz2,
                                       const float* coords, int B, int N, int K, int levels, float base_scale,
                                       float* vox, float* knn_sel, int32_t* knn_slot, double* moments,
                                       int8_t* dbg_cube, void* stream) {
-    if (!corr_val || !corr_idx || !xyz2p || !coords || !vox || !knn_sel) return fail(PVRAFT_ERR_BAD_ARG, "corr_lookup: null pointer");
+    if (!corr_val || !corr_idx || !xyz2 || !coords || !vox || !knn_sel) return fail(PVRAFT_ERR_BAD_ARG, "corr_lookup: null pointer");
     if (B <= 0 || N <= 0) return fail(PVRAFT_ERR_BAD_ARG, "corr_lookup: B=%d N=%d", B, N);
     if (levels < 1 || levels > 4) return fail(PVRAFT_ERR_UNSUPPORTED, "corr_lookup: levels=%d (1..4 supported)", levels);
     if (!(base_scale > 0.f)) return fail(PVRAFT_ERR_BAD_ARG, "corr_lookup: base_scale must be > 0");
     LookupParams p{};
-    p.corr_val = corr_val; p.corr_idx = corr_idx; p.tab = reinterpret_cast<const float4*>(xyz2p); p.coords = coords;
+    p.corr_val = corr_val; p.corr_idx = corr_idx; p.xyz2 = xyz2; p.coords = coords;
     p.vox = vox; p.knn_sel = reinterpret_cast<float4*>(knn_sel); p.knn_slot = knn_slot; p.moments = moments;
     p.B = B; p.N = N; p.K = K; p.levels = levels;
     bool pow2 = true;

@@ -34,7 +34,10 @@ static int tile_grid(int B, int N, size_t smem) {
     const long long tiles = (long long)B * ((N + kTP - 1) / kTP);
     int occ = (int)((size_t)kSmemBudget / (smem + 1024));
     occ = occ < 1 ? 1 : (occ > 4 ? 4 : occ);
-    long long g = (long long)sm_count() * occ;
+    // persistent CTAs: keep >= ~3 tiles per CTA so that the one-off weight staging is amortised
+    long long per_sm = tiles / ((long long)sm_count() * 3);
+    per_sm = per_sm < 1 ? 1 : (per_sm > occ ? occ : per_sm);
+    long long g = (long long)sm_count() * per_sm;
     if (g > tiles) g = tiles;
     return (int)(g < 1 ? 1 : g);
 }
@@ -62,7 +65,7 @@ __device__ __forceinline__ void flush_stats(double* s_g /*[16] smem*/, double* g
 // ---------------------------------------------------------------------------------------------------
 struct LinearParams {
     pvraft_linear_args a;
-    int KD, WS, AS, passes;
+    int KD, WS, CP, AS, passes;
 };
 
 __global__ void __launch_bounds__(kMlpThreads) k_linear(const LinearParams P) {
@@ -70,14 +73,14 @@ __global__ void __launch_bounds__(kMlpThreads) k_linear(const LinearParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_w = reinterpret_cast<float*>(smem_raw);
     float* s_bias = s_w + P.KD * P.WS;
-    float* s_scale = s_bias + P.WS;
+    float* s_scale = s_bias + P.CP;
     float* s_shift = s_scale + P.KD;
     float* s_act = s_shift + P.KD;
     double* s_g = reinterpret_cast<double*>(s_act + kTP * P.AS);   // [16]
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
 
-    stage_weight(s_w, P.KD, P.WS, a.weight, a.cout, a.w_ld > 0 ? a.w_ld : a.cin, 0, a.cin);
-    stage_vector(s_bias, P.WS, a.bias, a.cout);
+    stage_weight(s_w, P.KD, P.WS, P.CP, a.weight, a.cout, a.w_ld > 0 ? a.w_ld : a.cin, 0, a.cin);
+    stage_vector(s_bias, P.CP, a.bias, a.cout);
 
     double dS[8], dSS[8];
     int ch[8];
@@ -258,19 +261,20 @@ struct CorrFeatSmem {
     int r1, sel, r3, total;
 };
 constexpr int kAS128 = 132, kAS64 = 68;
+constexpr int kWS64 = 68, kWS128 = 132;   // wstride(64), wstride(128)
 
 __host__ __device__ inline CorrFeatSmem corrfeat_layout() {
     CorrFeatSmem L{};
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
-    L.w_out = take(128 * 64); L.b_out = take(64);
+    L.w_out = take(128 * kWS64); L.b_out = take(64);
     L.w_knn = take(4 * 64); L.b_knn = take(64);
-    L.w_kout = take(64 * 64); L.b_kout = take(64);
+    L.w_kout = take(64 * kWS64); L.b_kout = take(64);
     L.g1_scale = take(128); L.g1_shift = take(128);
     L.wk_eff = take(4 * 64); L.bk_eff = take(64);
-    L.w_cc = take(64 * 64); L.b_cc = take(64);
+    L.w_cc = take(64 * kWS64); L.b_cc = take(64);
     L.w_cf = take(4 * 64); L.b_cf = take(64);
-    L.w_cm = take(128 * 64); L.b_cm = take(64);
+    L.w_cm = take(128 * kWS64); L.b_cm = take(64);
     L.r1 = take(kTP * kAS128);      // GN'd y1 tile, later [cor | flo]
     L.sel = take(kTP * 32 * 4);     // kNN 4-vectors
     L.r3 = take(kTP * kAS64);       // kNN pooled feature, later the correlation feature
@@ -289,19 +293,19 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_corrfeat(const pvraft_corrfe
     const bool do_motion = a.motion != nullptr;
 
     if (do_feat) {
-        stage_weight(S + L.w_out, 128, 64, a.w_out, 64, 128, 0, 128);
+        stage_weight(S + L.w_out, 128, kWS64, 64, a.w_out, 64, 128, 0, 128);
         stage_vector(S + L.b_out, 64, a.b_out, 64);
-        stage_weight(S + L.w_knn, 4, 64, a.w_knn, 64, 4, 0, 4);
+        stage_weight(S + L.w_knn, 4, 64, 64, a.w_knn, 64, 4, 0, 4);
         stage_vector(S + L.b_knn, 64, a.b_knn, 64);
-        stage_weight(S + L.w_kout, 64, 64, a.w_kout, 64, 64, 0, 64);
+        stage_weight(S + L.w_kout, 64, kWS64, 64, a.w_kout, 64, 64, 0, 64);
         stage_vector(S + L.b_kout, 64, a.b_kout, 64);
     }
     if (do_motion) {
-        stage_weight(S + L.w_cc, 64, 64, a.w_cc, 64, 64, 0, 64);
+        stage_weight(S + L.w_cc, 64, kWS64, 64, a.w_cc, 64, 64, 0, 64);
         stage_vector(S + L.b_cc, 64, a.b_cc, 64);
-        stage_weight(S + L.w_cf, 4, 64, a.w_cf, 64, 3, 0, 3);
+        stage_weight(S + L.w_cf, 4, 64, 64, a.w_cf, 64, 3, 0, 3);
         stage_vector(S + L.b_cf, 64, a.b_cf, 64);
-        stage_weight(S + L.w_cm, 128, 64, a.w_cm, 61, 128, 0, 128);
+        stage_weight(S + L.w_cm, 128, kWS64, 64, a.w_cm, 61, 128, 0, 128);
         stage_vector(S + L.b_cm, 64, a.b_cm, 61);
     }
     const float slope1 = do_feat ? __ldg(a.prelu1) : 0.f;
@@ -376,7 +380,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_corrfeat(const pvraft_corrfe
             for (int p = 0; p < 4; ++p)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) vf[p][c] = 0.f;
-            tile_gemm<1>(S + L.r1, kAS128, S + L.w_out, 64, 128, vf);
+            tile_gemm<1>(S + L.r1, kAS128, S + L.w_out, kWS64, 128, vf);
             // ---- kNN branch: (GN-folded) 4->64 conv, PReLU, max over the 32 neighbours -----------------
             {
                 float4 wk[4];
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_corrfeat(const pvraft_corrfe
             for (int p = 0; p < 4; ++p)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) kf[p][c] = 0.f;
-            tile_gemm<1>(S + L.r3, kAS64, S + L.w_kout, 64, 64, kf);
+            tile_gemm<1>(S + L.r3, kAS64, S + L.w_kout, kWS64, 64, kf);
             const float4 bo = *reinterpret_cast<const float4*>(S + L.b_out + tx * 4);
             const float4 bko = *reinterpret_cast<const float4*>(S + L.b_kout + tx * 4);
 #pragma unroll
@@ -449,7 +453,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_corrfeat(const pvraft_corrfe
             for (int p = 0; p < 4; ++p)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) cor[p][c] = 0.f;
-            tile_gemm<1>(S + L.r3, kAS64, S + L.w_cc, 64, 64, cor);
+            tile_gemm<1>(S + L.r3, kAS64, S + L.w_cc, kWS64, 64, cor);
             const float4 bcc = *reinterpret_cast<const float4*>(S + L.b_cc + tx * 4);
             const float4 bcf = *reinterpret_cast<const float4*>(S + L.b_cf + tx * 4);
             float4 wf[3];
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_corrfeat(const pvraft_corrfe
             for (int p = 0; p < 4; ++p)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) mo[p][c] = 0.f;
-            tile_gemm<1>(S + L.r1, kAS128, S + L.w_cm, 64, 128, mo);
+            tile_gemm<1>(S + L.r1, kAS128, S + L.w_cm, kWS64, 128, mo);
             const float4 bcm = *reinterpret_cast<const float4*>(S + L.b_cm + tx * 4);
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
@@ -501,7 +505,7 @@ __host__ __device__ inline GruSmem gru_layout() {
     GruSmem L{};
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
-    L.w_zr = take(192 * 128); L.w_qx = take(128 * 64); L.w_qh = take(64 * 64);
+    L.w_zr = take(192 * kWS128); L.w_qx = take(128 * kWS64); L.w_qh = take(64 * kWS64);
     L.b_z = take(64); L.b_r = take(64); L.b_q = take(64);
     L.act = take(kTP * kAS192); L.rh = take(kTP * kAS64);
     L.total = o;
@@ -515,13 +519,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_gru(const pvraft_gru_args a)
     float* S = reinterpret_cast<float*>(smem_raw);
     const GruSmem L = gru_layout();
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    // [z | r] weights side by side: k-major [192][128]
-    for (int i = tid; i < 192 * 128; i += blockDim.x) {
-        const int k = i >> 7, c = i & 127;
-        S[L.w_zr + i] = c < 64 ? __ldg(a.w_z + (size_t)c * 192 + k) : __ldg(a.w_r + (size_t)(c - 64) * 192 + k);
-    }
-    stage_weight(S + L.w_qx, 128, 64, a.w_q, 64, 192, 64, 128);   // columns 64..191 act on x = [inp, motion]
-    stage_weight(S + L.w_qh, 64, 64, a.w_q, 64, 192, 0, 64);      // columns 0..63 act on r*h
+    // [z | r] weights side by side, k-major [192][128 (+4)]
+    stage_weight(S + L.w_zr, 192, kWS128, 64, a.w_z, 64, 192, 0, 192);
+    stage_weight(S + L.w_zr + 64, 192, kWS128, 64, a.w_r, 64, 192, 0, 192);
+    stage_weight(S + L.w_qx, 128, kWS64, 64, a.w_q, 64, 192, 64, 128);   // columns 64..191 act on x = [inp, motion]
+    stage_weight(S + L.w_qh, 64, kWS64, 64, a.w_q, 64, 192, 0, 64);      // columns 0..63 act on r*h
     stage_vector(S + L.b_z, 64, a.b_z, 64);
     stage_vector(S + L.b_r, 64, a.b_r, 64);
     stage_vector(S + L.b_q, 64, a.b_q, 64);
@@ -545,7 +547,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_gru(const pvraft_gru_args a)
         for (int p = 0; p < 4; ++p)
 #pragma unroll
             for (int c = 0; c < 8; ++c) zr[p][c] = 0.f;
-        tile_gemm<2>(S + L.act, kAS192, S + L.w_zr, 128, 192, zr);
+        tile_gemm<2>(S + L.act, kAS192, S + L.w_zr, kWS128, 192, zr);
         const float4 bz = *reinterpret_cast<const float4*>(S + L.b_z + tx * 4);
         const float4 br = *reinterpret_cast<const float4*>(S + L.b_r + tx * 4);
         float z[4][4], h[4][4];
@@ -566,8 +568,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_gru(const pvraft_gru_args a)
         for (int p = 0; p < 4; ++p)
 #pragma unroll
             for (int c = 0; c < 4; ++c) q[p][c] = 0.f;
-        tile_gemm<1>(S + L.rh, kAS64, S + L.w_qh, 64, 64, q);
-        tile_gemm<1>(S + L.act + 64, kAS192, S + L.w_qx, 64, 128, q);
+        tile_gemm<1>(S + L.rh, kAS64, S + L.w_qh, kWS64, 64, q);
+        tile_gemm<1>(S + L.act + 64, kAS192, S + L.w_qx, kWS64, 128, q);
         const float4 bq = *reinterpret_cast<const float4*>(S + L.b_q + tx * 4);
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
@@ -591,8 +593,8 @@ __host__ __device__ inline FlowOutSmem flowout_layout() {
     FlowOutSmem L{};
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
-    L.w_c1 = take(64 * 64); L.b_c1 = take(64);
-    L.w_o0 = take(128 * 64); L.b_o0 = take(64);
+    L.w_c1 = take(64 * kWS64); L.b_c1 = take(64);
+    L.w_o0 = take(128 * kWS64); L.b_o0 = take(64);
     L.w_o2 = take(64 * 4); L.b_o2 = take(4);
     L.scale = take(64); L.shift = take(64);
     L.cat = take(kTP * kAS128); L.tmp = take(kTP * kAS64);
@@ -605,11 +607,11 @@ __global__ void __launch_bounds__(kMlpThreads) k_flowout(const pvraft_flowout_ar
     float* S = reinterpret_cast<float*>(smem_raw);
     const FlowOutSmem L = flowout_layout();
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    stage_weight(S + L.w_c1, 64, 64, a.w_c1, 64, 64, 0, 64);
+    stage_weight(S + L.w_c1, 64, kWS64, 64, a.w_c1, 64, 64, 0, 64);
     stage_vector(S + L.b_c1, 64, a.b_c1, 64);
-    stage_weight(S + L.w_o0, 128, 64, a.w_o0, 64, 128, 0, 128);
+    stage_weight(S + L.w_o0, 128, kWS64, 64, a.w_o0, 64, 128, 0, 128);
     stage_vector(S + L.b_o0, 64, a.b_o0, 64);
-    stage_weight(S + L.w_o2, 64, 4, a.w_o2, 3, 64, 0, 64);
+    stage_weight(S + L.w_o2, 64, 4, 4, a.w_o2, 3, 64, 0, 64);
     stage_vector(S + L.b_o2, 4, a.b_o2, 3);
     int cur_b = -1;
     for (TileIter it(a.B, a.N); it.valid(); ++it.t) {
@@ -648,7 +650,7 @@ __global__ void __launch_bounds__(kMlpThreads) k_flowout(const pvraft_flowout_ar
         for (int p = 0; p < 4; ++p)
 #pragma unroll
             for (int c = 0; c < 4; ++c) c1[p][c] = 0.f;
-        tile_gemm<1>(S + L.tmp, kAS64, S + L.w_c1, 64, 64, c1);
+        tile_gemm<1>(S + L.tmp, kAS64, S + L.w_c1, kWS64, 64, c1);
         const float4 bc1 = *reinterpret_cast<const float4*>(S + L.b_c1 + tx * 4);
 #pragma unroll
         for (int p = 0; p < 4; ++p)
@@ -660,7 +662,7 @@ __global__ void __launch_bounds__(kMlpThreads) k_flowout(const pvraft_flowout_ar
         for (int p = 0; p < 4; ++p)
 #pragma unroll
             for (int c = 0; c < 4; ++c) o0[p][c] = 0.f;
-        tile_gemm<1>(S + L.cat, kAS128, S + L.w_o0, 64, 128, o0);
+        tile_gemm<1>(S + L.cat, kAS128, S + L.w_o0, kWS64, 128, o0);
         const float4 bo0 = *reinterpret_cast<const float4*>(S + L.b_o0 + tx * 4);
 #pragma unroll
         for (int p = 0; p < 4; ++p)
@@ -702,10 +704,11 @@ extern "C" int pvraft_linear_fwd(const pvraft_linear_args* a, void* stream) {
     LinearParams P{};
     P.a = *a;
     P.KD = pad4(a->cin);
-    P.WS = pad64(a->cout);
+    P.CP = pad64(a->cout);
+    P.WS = wstride(P.CP);
     P.AS = act_stride(P.KD);
-    P.passes = P.WS / 64;
-    const size_t smem = sizeof(float) * ((size_t)P.KD * P.WS + P.WS + 2 * P.KD + (size_t)kTP * P.AS) + 16 * sizeof(double) + 16;
+    P.passes = P.CP / 64;
+    const size_t smem = sizeof(float) * ((size_t)P.KD * P.WS + P.CP + 2 * P.KD + (size_t)kTP * P.AS) + 16 * sizeof(double) + 16;
     int rc;
     if ((rc = opt_in_smem(k_linear, smem))) return rc;
     k_linear<<<tile_grid(a->B, a->N, smem), kMlpThreads, smem, (cudaStream_t)stream>>>(P);

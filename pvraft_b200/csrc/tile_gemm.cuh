@@ -44,13 +44,21 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ act, int AS,
     }
 }
 
-// Stage a [cout][cin] row-major global weight as k-major [KD][WS] in shared memory, zero padded
-// (rows cin..KD-1 and columns cout..WS-1 are zero).  `col0` selects a sub-range of input columns.
-__device__ __forceinline__ void stage_weight(float* __restrict__ dst, int KD, int WS, const float* __restrict__ src,
+// Stage a [cout][cin_total] row-major global weight (columns col0 .. col0+cin-1) as k-major [KD][WS] in shared
+// memory.  Global reads are coalesced (source order); the transposed shared-memory stores hit 8 banks because
+// WS = padded_cout + 4 (wstride()), i.e. a 4-way conflict instead of 32-way.  Rows cin..KD-1 and columns
+// cout..CP-1 of the [KD][CP] window are zero filled.
+__device__ __forceinline__ void stage_weight(float* __restrict__ dst, int KD, int WS, int CP, const float* __restrict__ src,
                                              int cout, int cin_total, int col0, int cin) {
-    for (int i = threadIdx.x; i < KD * WS; i += blockDim.x) {
-        const int k = i / WS, c = i - k * WS;
-        dst[i] = (k < cin && c < cout) ? __ldg(src + (size_t)c * cin_total + col0 + k) : 0.f;
+    for (int i = threadIdx.x; i < cout * cin; i += blockDim.x) {
+        const int c = i / cin, k = i - c * cin;
+        dst[k * WS + c] = __ldg(src + (size_t)c * cin_total + col0 + k);
+    }
+    if (KD > cin || CP > cout) {
+        for (int i = threadIdx.x; i < KD * CP; i += blockDim.x) {
+            const int k = i / CP, c = i - k * CP;
+            if (k >= cin || c >= cout) dst[k * WS + c] = 0.f;
+        }
     }
 }
 
@@ -65,6 +73,8 @@ __host__ __device__ __forceinline__ int act_stride(int k_pad) {
     return s;
 }
 
+// row stride of a k-major weight tile with `cp` (multiple of 32) padded output channels
+__host__ __device__ __forceinline__ int wstride(int cp) { return cp + 4; }
 __host__ __device__ __forceinline__ int pad4(int x) { return (x + 3) & ~3; }
 __host__ __device__ __forceinline__ int pad64(int x) { return (x + 63) & ~63; }
 

@@ -43,11 +43,13 @@ def new_stats(b, device, n=1):
     return torch.zeros(n, b, 8, 2, dtype=torch.float64, device=device)
 
 
-def pad_xyz(xyz):
-    b, n, _ = xyz.shape
-    out = torch.empty(b, n, 4, dtype=torch.float32, device=xyz.device)
-    _count(lib().pvraft_pad_xyz(_p(xyz), b * n, _p(out), _stream()), 'pad_xyz')
-    return out
+def corr_reorder(val, idx):
+    """Bank-aware permutation of every row of the truncated state (val [B,N,K] f32, idx [B,N,K] int32)."""
+    b, n, k = val.shape
+    val_out, idx_out = torch.empty_like(val), torch.empty_like(idx)
+    _count(lib().pvraft_corr_reorder(_p(val), _p(idx, torch.int32), b * n, k, _p(val_out), _p(idx_out, torch.int32), _stream()),
+           'corr_reorder')
+    return val_out, idx_out
 
 
 def corr_topk(corr, k):
@@ -59,7 +61,7 @@ def corr_topk(corr, k):
     return val, idx
 
 
-def corr_lookup(corr_val, corr_idx, xyz2p, coords, levels, base_scale, vox=None, knn_sel=None, moments=None,
+def corr_lookup(corr_val, corr_idx, xyz2, coords, levels, base_scale, vox=None, knn_sel=None, moments=None,
                 want_slots=False, want_cube=False):
     """-> dict(vox [B,N,levels*27], knn_sel [B,N,32,4], moments [B,16] f64, [knn_slot], [cube])."""
     b, n, k = corr_val.shape
@@ -72,7 +74,7 @@ def corr_lookup(corr_val, corr_idx, xyz2p, coords, levels, base_scale, vox=None,
         moments = torch.zeros(b, MOMENTS, dtype=torch.float64, device=dev)
     slots = torch.empty(b, n, KNN, dtype=torch.int32, device=dev) if want_slots else None
     cube = torch.empty(b, n, k, levels, dtype=torch.int8, device=dev) if want_cube else None
-    _count(lib().pvraft_corr_lookup_fwd(_p(corr_val), _p(corr_idx, torch.int32), _p(xyz2p), _p(coords), b, n, k, levels,
+    _count(lib().pvraft_corr_lookup_fwd(_p(corr_val), _p(corr_idx, torch.int32), _p(xyz2), _p(coords), b, n, k, levels,
                                         float(base_scale), _p(vox), _p(knn_sel), _p(slots, torch.int32),
                                         _p(moments, torch.float64), _p(cube, torch.int8), _stream()), 'corr_lookup')
     return dict(vox=vox, knn_sel=knn_sel, moments=moments, knn_slot=slots, cube=cube)

@@ -32,6 +32,23 @@ def block_with_state(state, xyz2, dev, levels=3, base_scale=0.25, k=None):
     return cb
 
 
+def stored_state(cb):
+    """The state exactly as the block stores it (bank-aware candidate order): slot-level comparisons and the
+    sequential-sum order of the oracle are defined on this layout."""
+    val, idx = cb.corr_val.cpu(), cb.corr_idx.long().cpu()
+    # the arrangement is a permutation of every row
+    return O.CorrState(val, idx, cb.truncate_xyz2.cpu())
+
+
+def assert_row_permutation(cb, state):
+    a = torch.sort(cb.corr_idx.long().cpu(), -1).values
+    b = torch.sort(state.indices.long(), -1).values
+    assert torch.equal(a, b), 'reorder lost / duplicated candidates'
+    order = torch.argsort(cb.corr_idx.long().cpu(), -1)
+    order_ref = torch.argsort(state.indices.long(), -1)
+    assert torch.equal(torch.gather(cb.corr_val.cpu(), 2, order), torch.gather(state.truncated_corr, 2, order_ref))
+
+
 # ----------------------------------------------------------------------------------------------------
 # lookup kernel: indices, means, kNN selection, moments
 # ----------------------------------------------------------------------------------------------------
@@ -47,6 +64,8 @@ def test_lookup_against_oracle(dev, b, n, k, box, levels, scale):
     from pvraft_b200 import ops
     state, coords, xyz2 = O.synthetic_state(b, n, k, seed=n + k, box=box)
     cb = block_with_state(state, xyz2, dev, levels, scale)
+    assert_row_permutation(cb, state)
+    state = stored_state(cb)
     out = cb.lookup(coords.to(dev), want_slots=True, want_cube=True)
     torch.cuda.synchronize()
     # (1) cube index + validity of EVERY candidate, bit-exact (model/corr.py:52-62)
@@ -92,6 +111,7 @@ def test_lookup_duplicate_points_ties(dev):
     cand = torch.gather(xyz2.unsqueeze(1).expand(1, 256, 256, 3), 2, state.indices.unsqueeze(-1).expand(1, 256, 64, 3))
     state = O.CorrState(state.truncated_corr, state.indices, cand.contiguous())
     cb = block_with_state(state, xyz2, dev)
+    state = stored_state(cb)
     out = cb.lookup(coords.to(dev), want_slots=True)
     dist = O.knn_sqdist(state, coords)
     got = out['knn_slot'].cpu().long().sort(-1).values
@@ -107,6 +127,8 @@ def test_lookup_full_size_properties(dev):
     b, n, k = 2, 8192, 512
     state, coords, xyz2 = O.synthetic_state(b, n, k, seed=1, box=10.0)
     cb = block_with_state(state, xyz2, dev)
+    orig = state
+    state = stored_state(cb)
     out = cb.lookup(coords.to(dev), want_slots=True)
     torch.cuda.synchronize()
     rows = torch.randperm(n, generator=torch.Generator().manual_seed(0))[:512]
@@ -120,7 +142,7 @@ def test_lookup_full_size_properties(dev):
     # invariant: permuting the candidate order of every row changes neither the kNN set nor (beyond
     # rounding) the voxel means
     perm = torch.randperm(k, generator=torch.Generator().manual_seed(1))
-    cb2 = block_with_state(O.CorrState(state.truncated_corr[..., perm], state.indices[..., perm], None), xyz2, dev)
+    cb2 = block_with_state(O.CorrState(orig.truncated_corr[..., perm], orig.indices[..., perm], None), xyz2, dev)
     out2 = cb2.lookup(coords.to(dev), want_slots=True)
     assert rel_err(out2['vox'], out['vox']) < 1e-5
     a = torch.gather(cb.corr_idx, 2, out['knn_slot'].long()).sort(-1).values
@@ -197,7 +219,7 @@ def install_golden_state(m, arr, dev):
         eq = (txyz[bi].reshape(n * k, 1, 3) == pc2[bi].unsqueeze(0)).all(-1)
         idx[bi] = eq.float().argmax(-1).reshape(n, k)
     m.corr_block.set_state(arr['truncated_corr'].to(dev), idx.to(dev), pc2.to(dev))
-    assert torch.equal(m.corr_block.truncate_xyz2.cpu(), txyz)
+    assert torch.equal(m.corr_block.truncate_xyz2.cpu().sort(2).values, txyz.sort(2).values)
 
 
 def golden_graph(arr, dev):

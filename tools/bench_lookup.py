@@ -30,7 +30,8 @@ for box in a.box:
     idx = ((start + torch.arange(k, device=dev).view(1, 1, k) * step) % n).to(torch.int32).contiguous()
     coords = xyz2[:, torch.randperm(n, device=dev, generator=g)] + 0.2 * (torch.rand(b, n, 3, device=dev, generator=g) * 2 - 1)
     corr = torch.sort(torch.randn(b, n, k, device=dev, generator=g) * 5 + 20, dim=2, descending=True).values.contiguous()
-    tab = ops.pad_xyz(xyz2.contiguous())
+    tab = xyz2.contiguous()
+    corr, idx = ops.corr_reorder(corr, idx)
     coords = coords.contiguous()
     out = ops.corr_lookup(corr, idx, tab, coords, 3, 0.25)
     torch.cuda.synchronize()
