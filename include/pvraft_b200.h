@@ -56,10 +56,12 @@ PVRAFT_API const char* pvraft_last_error_string(void);
 PVRAFT_API int pvraft_device_info(int* sm_count, int* smem_optin_bytes);
 
 /* ------------------------------------------------------------------------------------------------
- * Correlation truncation: per-row top-K (sorted descending) of a dense correlation matrix.
+ * Correlation truncation: the K largest entries of every row of a dense correlation matrix.
  * Replaces torch.topk(corr, k, dim=2, sorted=True) in CorrBlock.init_module, model/corr.py:37-40.
- *   corr [B,N,M] -> val [B,N,K] f32, idx [B,N,K] int32 (column ids; ties: lowest column first)
- * Requires 32 <= K <= min(M, 1024); M*4 bytes must fit shared memory (M <= 49152).
+ *   corr [B,N,M] -> val [B,N,K] f32, idx [B,N,K] int32 column ids, written in ASCENDING COLUMN order
+ *   (value ties at the K-th place: lowest columns win).  The reference's descending-value order carries
+ *   no meaning downstream; pvraft_corr_reorder rearranges every row for the lookup kernel anyway.
+ * Requires 1 <= K <= min(M, 1024) and M <= 49152 (the row is staged in shared memory).
  * --------------------------------------------------------------------------------------------- */
 PVRAFT_API int pvraft_corr_topk_fwd(const float* corr, int B, int N, int M, int K, float* val, int32_t* idx, void* stream);
 
@@ -77,7 +79,8 @@ PVRAFT_API int pvraft_corr_reorder(const float* val_in, const int32_t* idx_in, i
  * every point.  Replaces CorrBlock.get_voxel_feature up to (not incl.) out_conv, model/corr.py:47-71,
  * and CorrBlock.get_knn_feature up to (not incl.) knn_conv, model/corr.py:75-91.
  *   corr_val [B,N,K] f32, corr_idx [B,N,K] int32 (rows of xyz2), xyz2 [B,N,3], coords [B,N,3]
- *   -> vox      [B,N,levels*27]  channel = level*27 + cell; mean corr of the candidates whose
+ *   -> vox      [B,N,vox_ld]     (vox_ld >= levels*27, 0 = dense; pad columns are written as zeros so that the
+ *                                consumer can read rows with 128-bit loads)  channel = level*27 + cell; mean corr of the candidates whose
  *                                round((xyz-coords)/r_level) lies in {-1,0,1}^3  (round-half-even,
  *                                true fp32 division; r_level = base_scale * 2^level)
  *   -> knn_sel  [B,N,32,4]       (corr, dx, dy, dz) of the 32 candidates nearest to coords
@@ -91,7 +94,7 @@ PVRAFT_API int pvraft_corr_reorder(const float* val_in, const int32_t* idx_in, i
  * K in {32,64,128,256,512,1024}; 1 <= levels <= 4; knn fixed at 32.
  * --------------------------------------------------------------------------------------------- */
 PVRAFT_API int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr_idx, const float* xyz2, const float* coords,
-                           int B, int N, int K, int levels, float base_scale, float* vox, float* knn_sel,
+                           int B, int N, int K, int levels, float base_scale, float* vox, int vox_ld, float* knn_sel,
                            int32_t* knn_slot, double* moments, int8_t* dbg_cube, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -123,8 +126,9 @@ typedef struct pvraft_linear_args {
     int in_mode;            /* pvraft_in_mode */
     int in_act;             /* pvraft_act applied after the input GroupNorm */
     float in_slope;
-    const float* weight;    /* [cout,cin] row-major; row stride w_ld floats (0 = cin): lets fc1.weight[:, :cin] be used in place */
+    const float* weight;    /* [cout,w_cin] row-major; row stride w_ld floats (0 = w_cin): lets fc1.weight[:, :cin] be used in place */
     int w_ld;
+    int w_cin;              /* weight columns used (0 = cin); input columns w_cin..cin-1 are padding and are ignored */
     const float* bias;      /* [cout] or NULL */
     const float* residual;  /* [B,N,cout] added to the output after bias/activation, or NULL (model/refine.py:22) */
     int out_act;            /* pvraft_act applied to the output (NONE or RELU) */
@@ -234,17 +238,21 @@ typedef struct pvraft_flowout_args {
 PVRAFT_API int pvraft_flow_out_fwd(const pvraft_flowout_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Brute-force k nearest neighbours.  Backs knn_point (model/pointconv.py:28-39) and the adjacency
- * of Graph.construct_graph (model/flot/graph.py:53-60, which argsorts a full N x N matrix).
+ * k nearest neighbours.  Backs knn_point (model/pointconv.py:28-39) and the adjacency of
+ * Graph.construct_graph (model/flot/graph.py:53-60, which argsorts a full N x N matrix).
  *   xyz [B,N,3] (candidates), query [B,S,3] -> idx [B,S,k] int32 LOCAL candidate ids, unordered;
  *   rel [B,S,k,3] = xyz[idx] - query (the graph's edge features, graph.py:69-74), or NULL.
  * mode 0: distance = (|q|^2 + |x|^2) - 2 q.x      (graph.py:53-57 op order)
  * mode 1: distance = (-2 q.x + |q|^2) + |x|^2     (pointconv.py:21-24 op order)
  * with q.x = fma(qz,xz, fma(qy,xy, qx*xx)) and |.|^2 = (x*x+y*y)+z*z.  1 <= k <= 32, N >= k.
  * Ties at the k-th place: lowest candidate id.
+ * workspace: pvraft_knn_workspace_bytes(B, N) bytes of device scratch (16-byte aligned) enable the
+ * x-sorted sweep (N <= 16384); with workspace == NULL (or larger N) the brute-force kernel runs.  Both
+ * return the same set.
  * --------------------------------------------------------------------------------------------- */
+PVRAFT_API int64_t pvraft_knn_workspace_bytes(int B, int N);
 PVRAFT_API int pvraft_knn_fwd(const float* xyz, const float* query, int B, int N, int S, int k, int mode, int32_t* idx,
-                   float* rel, void* stream);
+                   float* rel, void* workspace, void* stream);
 
 /* sizeof() of the argument structs as compiled into the library (0 = linear, 1 = corrfeat, 2 = gru,
  * 3 = flowout; -1 otherwise): lets a foreign-language binding verify its struct layout at load time. */

@@ -97,7 +97,7 @@ def construct_graph(pc: torch.Tensor, k: int = KNN) -> Graph:
     gathered = torch.gather(pc.unsqueeze(1).expand(b, n, n, 3), 2,
                             nbr.unsqueeze(-1).expand(b, n, k_eff, 3))
     edge_feats = (gathered - centre).reshape(b * n * k_eff, 3)              # graph.py:69-74
-    offs = (torch.arange(b, dtype=torch.int64) * n).view(b, 1, 1)           # graph.py:77-79
+    offs = (torch.arange(b, dtype=torch.int64, device=pc.device) * n).view(b, 1, 1)   # graph.py:77-79
     edges = (nbr + offs).reshape(-1)
     return Graph(edges, edge_feats, k_eff, (b * n, b * n))
 
@@ -208,8 +208,8 @@ def voxel_means(state: CorrState, coords: torch.Tensor, num_levels: int, base_sc
         r = base_scale * (2 ** lvl)
         cube, valid = voxel_cube_index(state, coords, r)
         w = valid.to(state.truncated_corr.dtype)
-        s = torch.zeros(b, n, cells).scatter_add_(2, cube, state.truncated_corr * w)
-        c = torch.zeros(b, n, cells).scatter_add_(2, cube, w)
+        s = torch.zeros(b, n, cells, device=coords.device).scatter_add_(2, cube, state.truncated_corr * w)
+        c = torch.zeros(b, n, cells, device=coords.device).scatter_add_(2, cube, w)
         feats.append((s / torch.clamp(c, 1, n)).transpose(1, 2))
     return torch.cat(feats, dim=1).contiguous()
 

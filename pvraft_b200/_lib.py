@@ -25,7 +25,7 @@ MOMENTS = 16
 class LinearArgs(C.Structure):
     _fields_ = [('in_', VP), ('in_min', VP), ('in_stats', VP), ('in_gamma', VP), ('in_beta', VP),
                 ('in_count', C.c_double), ('in_mode', C.c_int), ('in_act', C.c_int), ('in_slope', C.c_float),
-                ('weight', VP), ('w_ld', C.c_int), ('bias', VP), ('residual', VP), ('out_act', C.c_int),
+                ('weight', VP), ('w_ld', C.c_int), ('w_cin', C.c_int), ('bias', VP), ('residual', VP), ('out_act', C.c_int),
                 ('out', VP), ('out_stats', VP), ('B', C.c_int), ('N', C.c_int), ('cin', C.c_int), ('cout', C.c_int)]
 
 
@@ -55,7 +55,7 @@ _SIGNATURES = {
     'pvraft_corr_topk_fwd': (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int, VP, VP, VP]),
     'pvraft_corr_reorder': (C.c_int, [VP, VP, C.c_int64, C.c_int, VP, VP, VP]),
     'pvraft_corr_lookup_fwd': (C.c_int, [VP, VP, VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
-                                         VP, VP, VP, VP, VP, VP]),
+                                         VP, C.c_int, VP, VP, VP, VP, VP]),
     'pvraft_linear_fwd': (C.c_int, [C.POINTER(LinearArgs), VP]),
     'pvraft_gn_act_fwd': (C.c_int, [VP, VP, VP, VP, C.c_double, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                     C.c_int, VP, VP]),
@@ -63,7 +63,8 @@ _SIGNATURES = {
     'pvraft_gru_fwd': (C.c_int, [C.POINTER(GruArgs), VP]),
     'pvraft_setconv_edge_fwd': (C.c_int, [VP, VP, VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, VP, VP, VP, VP]),
     'pvraft_flow_out_fwd': (C.c_int, [C.POINTER(FlowOutArgs), VP]),
-    'pvraft_knn_fwd': (C.c_int, [VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, VP, VP, VP]),
+    'pvraft_knn_workspace_bytes': (C.c_int64, [C.c_int, C.c_int]),
+    'pvraft_knn_fwd': (C.c_int, [VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, VP, VP, VP, VP]),
     'pvraft_sizeof': (C.c_int, [C.c_int]),
     'pvraft_transpose_fwd': (C.c_int, [VP, C.c_int, C.c_int, C.c_int, VP, VP]),
 }

@@ -119,7 +119,8 @@ class CorrBlock(nn.Module):
         lk = self.lookup(coords)
         stats = ops.new_stats(b, coords.device, 1)
         oc = self.out_conv
-        y1 = ops.linear(lk['vox'], _w(oc[0].weight), _w(oc[0].bias), out_stats=stats[0], out_act=ACT_NONE)
+        y1 = ops.linear(lk['vox'], _w(oc[0].weight), _w(oc[0].bias), w_cin=self.num_levels * 27, out_stats=stats[0],
+                        out_act=ACT_NONE)
         a = self.feature_args(lk, y1, stats[0], b, n)
         corr = torch.empty(b, n, 64, dtype=torch.float32, device=coords.device)
         a.corr_feat = ops._p(corr)
@@ -141,7 +142,7 @@ class CorrBlock(nn.Module):
         lk = self.lookup(coords)
         stats = ops.new_stats(b, coords.device, 1)
         oc = self.out_conv
-        y1 = ops.linear(lk['vox'], _w(oc[0].weight), _w(oc[0].bias), out_stats=stats[0])
+        y1 = ops.linear(lk['vox'], _w(oc[0].weight), _w(oc[0].bias), w_cin=self.num_levels * 27, out_stats=stats[0])
         act = ops.gn_act(y1, stats[0], _w(oc[1].weight), _w(oc[1].bias), float(n) * 16, ops.ACT_LRELU,
                          float(oc[2].weight.detach().reshape(-1)[0]))
         return ops.transpose(ops.linear(act, _w(oc[3].weight), _w(oc[3].bias)))

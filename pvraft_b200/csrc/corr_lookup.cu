@@ -41,6 +41,7 @@ struct LookupParams {
     int32_t* knn_slot;   // [B,N,32] or null
     double* moments;     // [B,16] or null
     int B, N, K, levels;
+    int vox_ld;          // floats per vox row (>= levels*27; the pad is zero-filled)
     float r[4];          // cell edge per level
     float inv_r[4];      // exact reciprocal when r is a power of two
     int warps;           // warps per block actually carved in shared memory
@@ -291,8 +292,9 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                     }
                 }
                 __syncwarp();
+                if (lane < p.vox_ld - L * 27) p.vox[pt * p.vox_ld + L * 27 + lane] = 0.f;   // zero the row padding
                 if (lane < 27) {
-                    float* vo = p.vox + pt * (L * 27);
+                    float* vo = p.vox + pt * p.vox_ld;
 #pragma unroll
                     for (int l = 0; l < 4; ++l) {
                         if (l < L) {
@@ -558,7 +560,7 @@ extern "C" int pvraft_corr_reorder(const float* val_in, const int32_t* idx_in, i
 
 extern "C" int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr_idx, const float* xyz2,
                                       const float* coords, int B, int N, int K, int levels, float base_scale,
-                                      float* vox, float* knn_sel, int32_t* knn_slot, double* moments,
+                                      float* vox, int vox_ld, float* knn_sel, int32_t* knn_slot, double* moments,
                                       int8_t* dbg_cube, void* stream) {
     if (!corr_val || !corr_idx || !xyz2 || !coords || !vox || !knn_sel) return fail(PVRAFT_ERR_BAD_ARG, "corr_lookup: null pointer");
     if (B <= 0 || N <= 0) return fail(PVRAFT_ERR_BAD_ARG, "corr_lookup: B=%d N=%d", B, N);
@@ -568,6 +570,8 @@ extern "C" int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr
     p.corr_val = corr_val; p.corr_idx = corr_idx; p.xyz2 = xyz2; p.coords = coords;
     p.vox = vox; p.knn_sel = reinterpret_cast<float4*>(knn_sel); p.knn_slot = knn_slot; p.moments = moments;
     p.B = B; p.N = N; p.K = K; p.levels = levels;
+    p.vox_ld = vox_ld > 0 ? vox_ld : levels * 27;
+    if (p.vox_ld < levels * 27 || p.vox_ld > levels * 27 + 32) return fail(PVRAFT_ERR_BAD_ARG, "corr_lookup: vox_ld=%d", vox_ld);
     bool pow2 = true;
     for (int l = 0; l < 4; ++l) {
         // model/corr.py:53: r = base_scale * 2**i evaluated in double, then used as an fp32 divisor

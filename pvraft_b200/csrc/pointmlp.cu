@@ -30,14 +30,15 @@ struct TileIter {
     __device__ int npts() const { const int r = N - p0(); return r < kTP ? r : kTP; }
 };
 
-static int tile_grid(int B, int N, size_t smem) {
+template <typename Kernel>
+static int tile_grid(Kernel k, int B, int N, size_t smem) {
     const long long tiles = (long long)B * ((N + kTP - 1) / kTP);
-    int occ = (int)((size_t)kSmemBudget / (smem + 1024));
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kMlpThreads, smem) != cudaSuccess) occ = 1;
     occ = occ < 1 ? 1 : (occ > 4 ? 4 : occ);
-    // persistent CTAs: keep >= ~3 tiles per CTA so that the one-off weight staging is amortised
-    long long per_sm = tiles / ((long long)sm_count() * 3);
-    per_sm = per_sm < 1 ? 1 : (per_sm > occ ? occ : per_sm);
-    long long g = (long long)sm_count() * per_sm;
+    // persistent CTAs, as many per SM as shared memory allows (<= 4): a CTA alternates between a load phase and
+    // a GEMM phase, so co-resident CTAs are what overlaps the two
+    long long g = (long long)sm_count() * occ;
     if (g > tiles) g = tiles;
     return (int)(g < 1 ? 1 : g);
 }
@@ -68,7 +69,57 @@ struct LinearParams {
     int KD, WS, CP, AS, passes;
 };
 
-__global__ void __launch_bounds__(kMlpThreads) k_linear(const LinearParams P) {
+template <int CM4>
+__device__ __forceinline__ void linear_compute(const LinearParams& P, const float* s_act, const float* s_w, const float* s_bias,
+                                               size_t row0, int npts, double (&dS)[8], double (&dSS)[8]) {
+    const pvraft_linear_args& a = P.a;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][CM4 * 4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int c = 0; c < CM4 * 4; ++c) acc[p][c] = 0.f;
+    tile_gemm<CM4>(s_act, P.AS, s_w, P.WS, P.KD, acc);
+#pragma unroll
+    for (int pass = 0; pass < CM4; ++pass) {
+        const int c0 = pass * 64 + tx * 4;
+        const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int pp = ty * 4 + p;
+            float y[4] = {acc[p][pass * 4 + 0] + bv.x, acc[p][pass * 4 + 1] + bv.y, acc[p][pass * 4 + 2] + bv.z,
+                          acc[p][pass * 4 + 3] + bv.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) y[c] = apply_act(y[c], a.out_act, 0.f);
+            if (pp < npts) {
+                float* o = a.out + (row0 + pp) * a.cout + c0;
+                if (a.residual) {
+                    const float* rs = a.residual + (row0 + pp) * a.cout + c0;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c0 + c < a.cout) y[c] += __ldg(rs + c);
+                }
+                if ((a.cout & 3) == 0 && c0 + 3 < a.cout) {
+                    *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c0 + c < a.cout) o[c] = y[c];
+                }
+                if (a.out_stats) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const double v = (double)y[c];
+                        dS[pass * 4 + c] += v;
+                        dSS[pass * 4 + c] += v * v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kMlpThreads, 2) k_linear(const LinearParams P) {
     const pvraft_linear_args& a = P.a;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_w = reinterpret_cast<float*>(smem_raw);
@@ -79,7 +130,8 @@ __global__ void __launch_bounds__(kMlpThreads) k_linear(const LinearParams P) {
     double* s_g = reinterpret_cast<double*>(s_act + kTP * P.AS);   // [16]
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
 
-    stage_weight(s_w, P.KD, P.WS, P.CP, a.weight, a.cout, a.w_ld > 0 ? a.w_ld : a.cin, 0, a.cin);
+    const int w_cin = a.w_cin > 0 ? a.w_cin : a.cin;
+    stage_weight(s_w, P.KD, P.WS, P.CP, a.weight, a.cout, a.w_ld > 0 ? a.w_ld : w_cin, 0, w_cin);
     stage_vector(s_bias, P.CP, a.bias, a.cout);
 
     double dS[8], dSS[8];
@@ -153,48 +205,9 @@ __global__ void __launch_bounds__(kMlpThreads) k_linear(const LinearParams P) {
             }
         }
         __syncthreads();
-        // ---- GEMM passes of 64 output channels --------------------------------------------------------
-        for (int pass = 0; pass < P.passes; ++pass) {
-            float acc[4][4];
-#pragma unroll
-            for (int p = 0; p < 4; ++p)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[p][c] = 0.f;
-            tile_gemm<1>(s_act, P.AS, s_w + pass * 64, P.WS, P.KD, acc);
-            const int c0 = pass * 64 + tx * 4;
-            const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0);
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                const int pp = ty * 4 + p;
-                float y[4] = {acc[p][0] + bv.x, acc[p][1] + bv.y, acc[p][2] + bv.z, acc[p][3] + bv.w};
-#pragma unroll
-                for (int c = 0; c < 4; ++c) y[c] = apply_act(y[c], a.out_act, 0.f);
-                if (pp < npts) {
-                    float* o = a.out + (row0 + pp) * a.cout + c0;
-                    if (a.residual) {
-                        const float* rs = a.residual + (row0 + pp) * a.cout + c0;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (c0 + c < a.cout) y[c] += __ldg(rs + c);
-                    }
-                    if ((a.cout & 3) == 0 && c0 + 3 < a.cout) {
-                        *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (c0 + c < a.cout) o[c] = y[c];
-                    }
-                    if (a.out_stats) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const double v = (double)y[c];
-                            dS[pass * 4 + c] += v;
-                            dSS[pass * 4 + c] += v * v;
-                        }
-                    }
-                }
-            }
-        }
+        // ---- GEMM: all (<= 128) output channels in one sweep over the activations + epilogue ------------------
+        if (P.passes == 2) linear_compute<2>(P, s_act, s_w, s_bias, row0, npts, dS, dSS);
+        else linear_compute<1>(P, s_act, s_w, s_bias, row0, npts, dS, dSS);
     }
     if (a.out_stats && cur_b >= 0) flush_stats(s_g, a.out_stats + (size_t)cur_b * 16, dS, dSS, ch, P.passes * 4, a.cout);
 }
@@ -528,20 +541,38 @@ __global__ void __launch_bounds__(kMlpThreads, 1) k_gru(const pvraft_gru_args a)
     stage_vector(S + L.b_r, 64, a.b_r, 64);
     stage_vector(S + L.b_q, 64, a.b_q, 64);
 
-    for (TileIter it(a.B, a.N); it.valid(); ++it.t) {
-        const int b = it.sample(), p0 = it.p0(), npts = it.npts();
-        const size_t row0 = (size_t)b * a.N + p0;
-        __syncthreads();
-        for (int i = tid; i < kTP * 48; i += blockDim.x) {
-            const int p = i / 48, k4 = i - p * 48;
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p < npts) {
+    // the next tile's [h | inp | motion] rows are fetched into registers while the current tile is in the GEMMs
+    float4 pf[12];
+    auto fetch = [&](const TileIter& t) {
+        const size_t r0 = (size_t)t.sample() * a.N + t.p0();
+        const int np = t.npts();
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+            const int i = tid + q * kMlpThreads, p = i / 48, k4 = i - p * 48;
+            pf[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p < np) {
                 const float* src = k4 < 16 ? a.net : (k4 < 32 ? a.inp : a.motion);
-                x = *reinterpret_cast<const float4*>(src + (row0 + p) * 64 + (k4 & 15) * 4);
+                pf[q] = __ldg(reinterpret_cast<const float4*>(src + (r0 + p) * 64 + (k4 & 15) * 4));
             }
-            *reinterpret_cast<float4*>(S + L.act + p * kAS192 + k4 * 4) = x;
+        }
+    };
+    TileIter it(a.B, a.N);
+    if (it.valid()) fetch(it);
+    for (; it.valid(); ++it.t) {
+        const int p0 = it.p0(), npts = it.npts();
+        const size_t row0 = (size_t)it.sample() * a.N + p0;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+            const int i = tid + q * kMlpThreads, p = i / 48, k4 = i - p * 48;
+            *reinterpret_cast<float4*>(S + L.act + p * kAS192 + k4 * 4) = pf[q];
         }
         __syncthreads();
+        {
+            TileIter nx = it;
+            ++nx.t;
+            if (nx.valid()) fetch(nx);
+        }
         float zr[4][8];
 #pragma unroll
         for (int p = 0; p < 4; ++p)
@@ -602,7 +633,7 @@ __host__ __device__ inline FlowOutSmem flowout_layout() {
     return L;
 }
 
-__global__ void __launch_bounds__(kMlpThreads) k_flowout(const pvraft_flowout_args a) {
+__global__ void __launch_bounds__(kMlpThreads, 2) k_flowout(const pvraft_flowout_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* S = reinterpret_cast<float*>(smem_raw);
     const FlowOutSmem L = flowout_layout();
@@ -711,7 +742,7 @@ extern "C" int pvraft_linear_fwd(const pvraft_linear_args* a, void* stream) {
     const size_t smem = sizeof(float) * ((size_t)P.KD * P.WS + P.CP + 2 * P.KD + (size_t)kTP * P.AS) + 16 * sizeof(double) + 16;
     int rc;
     if ((rc = opt_in_smem(k_linear, smem))) return rc;
-    k_linear<<<tile_grid(a->B, a->N, smem), kMlpThreads, smem, (cudaStream_t)stream>>>(P);
+    k_linear<<<tile_grid(k_linear, a->B, a->N, smem), kMlpThreads, smem, (cudaStream_t)stream>>>(P);
     return check_launch("linear");
 }
 
@@ -744,7 +775,7 @@ extern "C" int pvraft_corr_feature_fwd(const pvraft_corrfeat_args* a, void* stre
     const size_t smem = (size_t)corrfeat_layout().total * sizeof(float);
     int rc;
     if ((rc = opt_in_smem(k_corrfeat, smem))) return rc;
-    k_corrfeat<<<tile_grid(a->B, a->N, smem), kMlpThreads, smem, (cudaStream_t)stream>>>(*a);
+    k_corrfeat<<<tile_grid(k_corrfeat, a->B, a->N, smem), kMlpThreads, smem, (cudaStream_t)stream>>>(*a);
     return check_launch("corr_feature");
 }
 
@@ -755,7 +786,7 @@ extern "C" int pvraft_gru_fwd(const pvraft_gru_args* a, void* stream) {
     const size_t smem = (size_t)gru_layout().total * sizeof(float);
     int rc;
     if ((rc = opt_in_smem(k_gru, smem))) return rc;
-    k_gru<<<tile_grid(a->B, a->N, smem), kMlpThreads, smem, (cudaStream_t)stream>>>(*a);
+    k_gru<<<tile_grid(k_gru, a->B, a->N, smem), kMlpThreads, smem, (cudaStream_t)stream>>>(*a);
     return check_launch("gru");
 }
 
@@ -768,6 +799,6 @@ extern "C" int pvraft_flow_out_fwd(const pvraft_flowout_args* a, void* stream) {
     const size_t smem = (size_t)flowout_layout().total * sizeof(float);
     int rc;
     if ((rc = opt_in_smem(k_flowout, smem))) return rc;
-    k_flowout<<<tile_grid(a->B, a->N, smem), kMlpThreads, smem, (cudaStream_t)stream>>>(*a);
+    k_flowout<<<tile_grid(k_flowout, a->B, a->N, smem), kMlpThreads, smem, (cudaStream_t)stream>>>(*a);
     return check_launch("flow_out");
 }

@@ -21,26 +21,45 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ act, int AS,
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const float* a0 = act + (ty * 4) * AS;
     const float* w0 = w + tx * 4;
-#pragma unroll 2
-    for (int k = 0; k < KD; k += 4) {
-        float4 a[4];
+    // software pipeline: the shared-memory fragments of chunk k+4 are fetched before the FMAs of chunk k
+    // (a CTA of 8 warps leaves only 2 warps per scheduler, too few to hide the LDS latency otherwise)
+    float4 a[4], wv[4][CM4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) a[p] = *reinterpret_cast<const float4*>(a0 + p * AS + k);
+    for (int p = 0; p < 4; ++p) a[p] = *reinterpret_cast<const float4*>(a0 + p * AS);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int g = 0; g < CM4; ++g) wv[kk][g] = *reinterpret_cast<const float4*>(w0 + kk * WS + g * 64);
+#pragma unroll 1
+    for (int k = 0; k < KD; k += 4) {
+        float4 an[4], wn[4][CM4];
+        const int kn = k + 4 < KD ? k + 4 : k;   // the last iteration re-reads its own chunk (harmless)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) an[p] = *reinterpret_cast<const float4*>(a0 + p * AS + kn);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int g = 0; g < CM4; ++g) wn[kk][g] = *reinterpret_cast<const float4*>(w0 + (kn + kk) * WS + g * 64);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
             for (int g = 0; g < CM4; ++g) {
-                const float4 wv = *reinterpret_cast<const float4*>(w0 + (k + kk) * WS + g * 64);
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
                     const float av = kk == 0 ? a[p].x : kk == 1 ? a[p].y : kk == 2 ? a[p].z : a[p].w;
-                    acc[p][g * 4 + 0] = fmaf(av, wv.x, acc[p][g * 4 + 0]);
-                    acc[p][g * 4 + 1] = fmaf(av, wv.y, acc[p][g * 4 + 1]);
-                    acc[p][g * 4 + 2] = fmaf(av, wv.z, acc[p][g * 4 + 2]);
-                    acc[p][g * 4 + 3] = fmaf(av, wv.w, acc[p][g * 4 + 3]);
+                    acc[p][g * 4 + 0] = fmaf(av, wv[kk][g].x, acc[p][g * 4 + 0]);
+                    acc[p][g * 4 + 1] = fmaf(av, wv[kk][g].y, acc[p][g * 4 + 1]);
+                    acc[p][g * 4 + 2] = fmaf(av, wv[kk][g].z, acc[p][g * 4 + 2]);
+                    acc[p][g * 4 + 3] = fmaf(av, wv[kk][g].w, acc[p][g * 4 + 3]);
                 }
             }
         }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) a[p] = an[p];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int g = 0; g < CM4; ++g) wv[kk][g] = wn[kk][g];
     }
 }
 

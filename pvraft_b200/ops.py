@@ -53,7 +53,7 @@ def corr_reorder(val, idx):
 
 
 def corr_topk(corr, k):
-    """corr [B,N,M] -> (val [B,N,K] f32 sorted desc, idx [B,N,K] int32)."""
+    """corr [B,N,M] -> (val [B,N,K] f32, idx [B,N,K] int32): the K largest per row, ascending column order."""
     b, n, m = corr.shape
     val = torch.empty(b, n, k, dtype=torch.float32, device=corr.device)
     idx = torch.empty(b, n, k, dtype=torch.int32, device=corr.device)
@@ -63,11 +63,12 @@ def corr_topk(corr, k):
 
 def corr_lookup(corr_val, corr_idx, xyz2, coords, levels, base_scale, vox=None, knn_sel=None, moments=None,
                 want_slots=False, want_cube=False):
-    """-> dict(vox [B,N,levels*27], knn_sel [B,N,32,4], moments [B,16] f64, [knn_slot], [cube])."""
+    """-> dict(vox [B,N,pad4(levels*27)], knn_sel [B,N,32,4], moments [B,16] f64, [knn_slot], [cube])."""
     b, n, k = corr_val.shape
     dev = corr_val.device
+    vox_ld = (levels * 27 + 3) // 4 * 4          # rows padded to a multiple of 4 floats (zero-filled by the kernel)
     if vox is None:
-        vox = torch.empty(b, n, levels * 27, dtype=torch.float32, device=dev)
+        vox = torch.empty(b, n, vox_ld, dtype=torch.float32, device=dev)
     if knn_sel is None:
         knn_sel = torch.empty(b, n, KNN, 4, dtype=torch.float32, device=dev)
     if moments is None:
@@ -75,12 +76,12 @@ def corr_lookup(corr_val, corr_idx, xyz2, coords, levels, base_scale, vox=None, 
     slots = torch.empty(b, n, KNN, dtype=torch.int32, device=dev) if want_slots else None
     cube = torch.empty(b, n, k, levels, dtype=torch.int8, device=dev) if want_cube else None
     _count(lib().pvraft_corr_lookup_fwd(_p(corr_val), _p(corr_idx, torch.int32), _p(xyz2), _p(coords), b, n, k, levels,
-                                        float(base_scale), _p(vox), _p(knn_sel), _p(slots, torch.int32),
+                                        float(base_scale), _p(vox), vox.shape[-1], _p(knn_sel), _p(slots, torch.int32),
                                         _p(moments, torch.float64), _p(cube, torch.int8), _stream()), 'corr_lookup')
     return dict(vox=vox, knn_sel=knn_sel, moments=moments, knn_slot=slots, cube=cube)
 
 
-def linear(x, weight, bias=None, *, cin=None, w_ld=0, in_mode=IN_PLAIN, in_min=None, in_stats=None, in_gamma=None,
+def linear(x, weight, bias=None, *, cin=None, w_ld=0, w_cin=0, in_mode=IN_PLAIN, in_min=None, in_stats=None, in_gamma=None,
            in_beta=None, in_count=0.0, in_act=ACT_NONE, in_slope=0.0, out_act=ACT_NONE, out=None, out_stats=None,
            residual=None, cout=None):
     """Fused [GN -> act ->] 1x1 conv [+bias] [-> ReLU] [+ residual] over x [B,N,cin] -> [B,N,cout]."""
@@ -90,7 +91,7 @@ def linear(x, weight, bias=None, *, cin=None, w_ld=0, in_mode=IN_PLAIN, in_min=N
     if out is None:
         out = torch.empty(b, n, cout, dtype=torch.float32, device=x.device)
     a = _lib.LinearArgs(_p(x), _p(in_min), _p(in_stats, torch.float64), _p(in_gamma), _p(in_beta), float(in_count),
-                        in_mode, in_act, float(in_slope), _p(weight), int(w_ld), _p(bias), _p(residual), out_act,
+                        in_mode, in_act, float(in_slope), _p(weight), int(w_ld), int(w_cin), _p(bias), _p(residual), out_act,
                         _p(out), _p(out_stats, torch.float64), b, n, cin, cout)
     _count(lib().pvraft_linear_fwd(C.byref(a), _stream()), 'linear')
     return out
@@ -135,14 +136,17 @@ def setconv_edge(fc1p, nbr, edge_feats, w_fc1, cin, stats, ymax=None, ymin=None)
     return ymax, ymin
 
 
-def knn(xyz, query, k, mode=0, want_rel=False):
+def knn(xyz, query, k, mode=0, want_rel=False, use_sweep=True):
     """-> int32 [B,S,k] local ids of the k nearest `xyz` points of every query (unordered)
     [, rel [B,S,k,3] = xyz[idx] - query]."""
     b, n, _ = xyz.shape
     s = query.shape[1]
     out = torch.empty(b, s, k, dtype=torch.int32, device=xyz.device)
     rel = torch.empty(b, s, k, 3, dtype=torch.float32, device=xyz.device) if want_rel else None
-    _count(lib().pvraft_knn_fwd(_p(xyz), _p(query), b, n, s, k, mode, _p(out, torch.int32), _p(rel), _stream()), 'knn')
+    ws_bytes = int(lib().pvraft_knn_workspace_bytes(b, n)) if use_sweep else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz.device) if ws_bytes > 0 else None
+    _count(lib().pvraft_knn_fwd(_p(xyz), _p(query), b, n, s, k, mode, _p(out, torch.int32), _p(rel),
+                                _p(ws, torch.uint8), _stream()), 'knn')
     return (out, rel) if want_rel else out
 
 
