@@ -165,7 +165,7 @@ def run_reference(a):
     bounded sample of cpu_sample(): the full pre-loop work + 4 of the 32 iterations at B=1, scaled to 32."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
-        return
+        return None
     threads = cpu_pick_threads()
     warm = min(a.warmup, 1)
     for _ in range(warm):
@@ -195,7 +195,7 @@ def run_reference(a):
                                    f'{threads} of {os.cpu_count()} host threads (fastest of a thread sweep)'},
         'e2e': {'value': value, 'unit': 'sample-iterations/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def workload_config(batch_per_gpu, world):
@@ -297,7 +297,7 @@ def run_native(a):
             pass
 
     if rank != 0:
-        return
+        return None
     cpu = None
     if world == 1 and not a.no_cpu:
         threads = cpu_pick_threads()
@@ -315,7 +315,23 @@ def run_native(a):
                 'd2h_bytes_per_step': B * N_POINTS * 3 * 4 * world, 'ms_per_step': ms_e2e / a.steps},
         'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
     }
-    print(json.dumps(line), flush=True)
+    return line
+
+
+class _QuietStdout:
+    """Libraries (NCCL's version banner, warnings) write to fd 1; the contract is ONE JSON line on stdout.
+    Route fd 1 to stderr while the benchmark runs and restore it for the final print."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 def main():
@@ -327,10 +343,12 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='samples per GPU')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     a = ap.parse_args()
-    if a.impl == 'reference':
-        run_reference(a)
-    else:
-        run_native(a)
+    with _QuietStdout():
+        line = run_reference(a) if a.impl == 'reference' else run_native(a)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == '__main__':

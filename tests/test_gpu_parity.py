@@ -59,6 +59,7 @@ def assert_row_permutation(cb, state):
     (1, 300, 32, 3.0, 2, 0.3),       # K = 32 (every candidate is a neighbour), non power-of-two scale, ragged N
     (1, 256, 256, 1.5, 4, 0.125),    # 4 levels
     (1, 2048, 1024, 4.0, 1, 0.5),    # K = 1024, single level
+    (1, 16384, 128, 12.0, 3, 0.25),  # N too large for the shared-memory xyz table: global-gather variant
 ])
 def test_lookup_against_oracle(dev, b, n, k, box, levels, scale):
     from pvraft_b200 import ops

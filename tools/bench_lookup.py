@@ -18,11 +18,14 @@ ap.add_argument('--k', type=int, default=512)
 ap.add_argument('--box', type=float, nargs='+', default=[10.0, 3.0])
 ap.add_argument('--reps', type=int, default=20)
 ap.add_argument('--profile', action='store_true')
+ap.add_argument('--sweep', action='store_true', help='BASELINE config 5: N in {2048..32768}, B sized so the state is >= 4x L2')
 a = ap.parse_args()
 dev = torch.device('cuda:0')
 peaks, kind = bench.measured_peaks()
-b, n, k = a.batch, a.points, a.k
-for box in a.box:
+cases = [(a.batch, a.points, a.k, box) for box in a.box]
+if a.sweep:
+    cases = [(64, 2048, 512, 10.0), (32, 4096, 512, 10.0), (16, 8192, 512, 10.0), (8, 16384, 512, 10.0), (4, 32768, 512, 10.0)]
+for b, n, k, box in cases:
     g = torch.Generator(device=dev).manual_seed(1)
     xyz2 = box * torch.rand(b, n, 3, device=dev, generator=g)
     start = torch.randint(0, n, (b, n, 1), device=dev, generator=g)
@@ -50,7 +53,7 @@ for box in a.box:
     ms = sorted(s.elapsed_time(e) for s, e in evs)
     med = ms[len(ms) // 2]
     alg = bench.alg_bytes_lookup(n, k) * b
-    valid = float((out['vox'].view(b, n, 3, 27) != 0).float().sum(-1).mean())
+    valid = float((out['vox'][..., :81].reshape(b, n, 3, 27) != 0).float().sum(-1).mean())
     print(json.dumps({'box': box, 'B': b, 'N': n, 'K': k, 'median_ms': med, 'min_ms': ms[0], 'us_per_sample': med * 1e3 / b,
                       'alg_GBps': alg / med / 1e6, 'frac_of_hbm_peak': alg / med / 1e6 / peaks['hbm_gbs'], 'peak': kind,
                       'nonempty_cells_per_level': valid}))
