@@ -56,6 +56,16 @@ PVRAFT_API const char* pvraft_last_error_string(void);
 PVRAFT_API int pvraft_device_info(int* sm_count, int* smem_optin_bytes);
 
 /* ------------------------------------------------------------------------------------------------
+ * All-pairs feature correlation on the tcgen05 tensor cores with an fp32-accurate 3xTF32 split.
+ * Replaces CorrBlock.calculate_corr, model/corr.py:95-100: corr[b,i,j] = <fmap1[b,i,:], fmap2[b,j,:]> / sqrt(C).
+ *   fmap1, fmap2 [B,N,C] POINT-major f32 -> corr [B,N,N] f32.   N % 128 == 0, C % 32 == 0.
+ *   workspace: pvraft_corr_matmul_workspace_bytes(B,N,C) bytes (16-byte aligned) for the hi/lo operand splits.
+ * --------------------------------------------------------------------------------------------- */
+PVRAFT_API int64_t pvraft_corr_matmul_workspace_bytes(int B, int N, int C);
+PVRAFT_API int pvraft_corr_matmul_fwd(const float* fmap1, const float* fmap2, int B, int N, int C, float* corr, void* workspace,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Correlation truncation: the K largest entries of every row of a dense correlation matrix.
  * Replaces torch.topk(corr, k, dim=2, sorted=True) in CorrBlock.init_module, model/corr.py:37-40.
  *   corr [B,N,M] -> val [B,N,K] f32, idx [B,N,K] int32 column ids, written in ASCENDING COLUMN order

@@ -52,19 +52,28 @@ class CorrBlock(nn.Module):
     # ------------------------------------------------------------------------------------------
     @staticmethod
     def calculate_corr(fmap1, fmap2):
-        """model/corr.py:95-100.  A plain library GEMM (cuBLAS via torch.matmul) -- the dense N x N
-        product is the one genuine large contraction of the model; fusing it with the top-K
-        selection in a tcgen05 kernel is the next step."""
+        """model/corr.py:95-100, kept for API parity (a plain library GEMM).  init_module uses the
+        tcgen05 kernel (ops.corr_matmul) whenever N % 128 == 0 and C % 32 == 0."""
         dim = fmap1.shape[1]
         corr = torch.matmul(fmap1.transpose(1, 2), fmap2)
         return corr / torch.sqrt(torch.tensor(dim).float())
 
     def init_module(self, fmap1, fmap2, xyz2):
-        """model/corr.py:31-42: build the truncated correlation state for one forward pass."""
+        """model/corr.py:31-42: build the truncated correlation state for one forward pass
+        (fmap1, fmap2 [B,C,N] channel-major as in the reference)."""
+        return self.init_module_pm(ops.transpose(fmap1.detach().contiguous().float()),
+                                   ops.transpose(fmap2.detach().contiguous().float()), xyz2)
+
+    def init_module_pm(self, fmap1_pm, fmap2_pm, xyz2):
+        """Same with point-major feature maps [B,N,C] (what the encoders produce natively)."""
         b, n_p, _ = xyz2.shape
         if n_p < self.truncate_k:
             raise ValueError(f'truncate_k={self.truncate_k} exceeds the number of points {n_p}')
-        corr = self.calculate_corr(fmap1.detach().float(), fmap2.detach().float()).contiguous()
+        c = fmap1_pm.shape[-1]
+        if n_p % 128 == 0 and c % 32 == 0:
+            corr = ops.corr_matmul(fmap1_pm, fmap2_pm)          # tcgen05, 3xTF32 (fp32-accurate)
+        else:                                                   # odd sizes: the library GEMM of calculate_corr
+            corr = self.calculate_corr(fmap1_pm.transpose(1, 2), fmap2_pm.transpose(1, 2)).contiguous()
         val, idx = ops.corr_topk(corr, self.truncate_k)
         self.corr_val, self.corr_idx = ops.corr_reorder(val, idx)
         self._xyz2 = xyz2.detach().contiguous().float()

@@ -52,6 +52,16 @@ def corr_reorder(val, idx):
     return val_out, idx_out
 
 
+def corr_matmul(fmap1_pm, fmap2_pm):
+    """Point-major feature maps [B,N,C] -> all-pairs correlation [B,N,N] / sqrt(C) on tcgen05 (3xTF32)."""
+    b, n, c = fmap1_pm.shape
+    corr = torch.empty(b, n, n, dtype=torch.float32, device=fmap1_pm.device)
+    ws = torch.empty(int(lib().pvraft_corr_matmul_workspace_bytes(b, n, c)), dtype=torch.uint8, device=fmap1_pm.device)
+    _count(lib().pvraft_corr_matmul_fwd(_p(fmap1_pm), _p(fmap2_pm), b, n, c, _p(corr), _p(ws, torch.uint8), _stream()),
+           'corr_matmul')
+    return corr
+
+
 def corr_topk(corr, k):
     """corr [B,N,M] -> (val [B,N,K] f32, idx [B,N,K] int32): the K largest per row, ascending column order."""
     b, n, m = corr.shape

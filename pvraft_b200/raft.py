@@ -30,9 +30,9 @@ class _RaftBase(nn.Module):
             raise ValueError('expected p = [xyz1 [B,N,3], xyz2 [B,N,3]]')
         xyz1 = xyz1.detach().contiguous().float()
         xyz2 = xyz2.detach().contiguous().float()
-        fmap1, graph = self.feature_extractor(xyz1)                      # RAFTSceneFlow.py:25
-        fmap2, _ = self.feature_extractor(xyz2)                          # :26
-        self.corr_block.init_module(fmap1, fmap2, xyz2)                  # :29
+        fmap1, graph = self.feature_extractor(xyz1, point_major=True)    # RAFTSceneFlow.py:25
+        fmap2, _ = self.feature_extractor(xyz2, point_major=True)        # :26
+        self.corr_block.init_module_pm(fmap1, fmap2, xyz2)               # :29
         # the reference rebuilds the same pc1 graph for the context encoder (:31); reuse it
         fct1, graph_context = self.context_extractor(xyz1, graph=graph, point_major=True)
         net = torch.tanh(fct1[..., :self.hidden_dim]).contiguous()       # :33-35 (point-major split)

@@ -339,3 +339,19 @@ def test_rsf_default_init_medium(dev):
     for it in range(iters):
         ref = arr[f'it{it}/flow']
         assert float((flows[it].cpu() - ref).abs().mean()) < 2e-3 * float(ref.abs().mean())
+
+
+@pytest.mark.parametrize('b,n,c', [(1, 128, 32), (2, 256, 128), (1, 1024, 128), (1, 384, 64)])
+def test_corr_matmul_tcgen05(dev, b, n, c):
+    """calculate_corr on tcgen05 with the 3xTF32 split: fp32-level agreement with an fp64 product."""
+    from pvraft_b200 import ops
+    g = torch.Generator().manual_seed(n + c)
+    f1 = torch.randn(b, n, c, generator=g) * 2.0
+    f2 = torch.randn(b, n, c, generator=g) * 2.0 + 0.3
+    got = ops.corr_matmul(f1.to(dev), f2.to(dev)).cpu()
+    want = torch.matmul(f1.double(), f2.double().transpose(1, 2)) / (c ** 0.5)
+    err = (got.double() - want).abs().max() / want.abs().max()
+    assert err < 2e-6, float(err)
+    # and against the reference's own fp32 formulation (model/corr.py:95-100)
+    ref32 = O.calculate_corr(f1.transpose(1, 2), f2.transpose(1, 2))
+    assert rel_err(got, ref32) < 5e-6
