@@ -149,6 +149,52 @@ typedef struct pvraft_linear_args {
 
 PVRAFT_API int pvraft_linear_fwd(const pvraft_linear_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * The same fused layer on the tcgen05 tensor cores (TMA + TMEM), fp32-accurate through a 3xTF32 operand split.
+ * Up to three activation sources are concatenated along K (e.g. [h | inp | motion] of the ConvGRU,
+ * model/update.py:32,36); the GroupNorm(+max/min selection)+activation prologue and the bias / ReLU / residual /
+ * GroupNorm-statistics epilogue match pvraft_linear_fwd; two extra epilogues implement the ConvGRU gates
+ * (model/update.py:34-39).  Requirements: points per sample N % 128 == 0; every source has a multiple of 32
+ * channels; weights pre-split with pvraft_tc_weight_split into hi/lo [n_pad, K] (n_pad = cout rounded up to 16, <= 128).
+ * --------------------------------------------------------------------------------------------- */
+typedef enum pvraft_tc_epilogue {
+    PVRAFT_TC_PLAIN = 0,   /* out = act(acc + bias) (+ residual), optional output statistics                  */
+    PVRAFT_TC_GRU_ZR = 1,  /* acc = [z|r] pre-activations (n_pad = 128): out = sigmoid(z), out2 = sigmoid(r) * h */
+    PVRAFT_TC_GRU_Q = 2    /* acc = q pre-activation: out = (1 - z) * h + z * tanh(acc + bias)                  */
+} pvraft_tc_epilogue;
+
+typedef struct pvraft_tc_linear_args {
+    const float* in[3];     /* activation sources [B,N,in_channels[i]]; unused entries NULL */
+    int in_channels[3];
+    const float* in_min;    /* per-channel minima paired with in[0] (GroupNorm prologue with max/min selection) or NULL */
+    const double* in_stats; /* [B,8,2] -> GroupNorm prologue on the (single) source, or NULL */
+    const float* in_gamma;
+    const float* in_beta;
+    double in_count;
+    int in_act;             /* pvraft_act */
+    float in_slope;
+    const float* w_hi;      /* [n_pad, K] tf32 high parts, K = sum of in_channels */
+    const float* w_lo;      /* [n_pad, K] tf32 low parts */
+    int n_pad, cout;
+    const float* bias;      /* [cout] or NULL (GRU_ZR: bias of z; GRU_Q: bias of q) */
+    const float* bias2;     /* GRU_ZR: bias of r */
+    int out_act;
+    const float* residual;  /* [B,N,cout] or NULL */
+    float* out;             /* [B,N,cout] */
+    float* out2;            /* GRU_ZR: r*h [B,N,64] */
+    const float* h;         /* GRU epilogues: previous hidden state [B,N,64] */
+    const float* z;         /* GRU_Q: update gate [B,N,64] */
+    double* out_stats;      /* [B,8,2] accumulated, or NULL */
+    int epilogue;           /* pvraft_tc_epilogue */
+    int B, N;
+} pvraft_tc_linear_args;
+
+PVRAFT_API int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream);
+/* hi = tf32(w), lo = tf32(w - hi) of the window w[0:rows, col0:col0+cols] of a row-major matrix with row stride ld,
+ * written zero-padded as [rows_pad, cols_pad]. */
+PVRAFT_API int pvraft_tc_weight_split(const float* w, int rows, int cols, int ld, int col0, int rows_pad, int cols_pad,
+                           float* hi, float* lo, void* stream);
+
 /* out[B,N,C] (or channel-major [B,C,N] when transpose_out != 0) = act(GN(in)) -- the trailing
  * GroupNorm+LeakyReLU of SetConv (model/flot/gconv.py:33,82-83) when nothing follows it. */
 PVRAFT_API int pvraft_gn_act_fwd(const float* in, const double* stats, const float* gamma, const float* beta, double count,
@@ -265,7 +311,7 @@ PVRAFT_API int pvraft_knn_fwd(const float* xyz, const float* query, int B, int N
                    float* rel, void* workspace, void* stream);
 
 /* sizeof() of the argument structs as compiled into the library (0 = linear, 1 = corrfeat, 2 = gru,
- * 3 = flowout; -1 otherwise): lets a foreign-language binding verify its struct layout at load time. */
+ * 3 = flowout, 4 = tc_linear; -1 otherwise): lets a foreign-language binding verify its struct layout at load time. */
 PVRAFT_API int pvraft_sizeof(int which);
 
 /* [B,C,N] <-> [B,N,C] transposes used at the reference-layout seams of the Python modules. */

@@ -29,6 +29,14 @@ class LinearArgs(C.Structure):
                 ('out', VP), ('out_stats', VP), ('B', C.c_int), ('N', C.c_int), ('cin', C.c_int), ('cout', C.c_int)]
 
 
+class TcLinearArgs(C.Structure):
+    _fields_ = [('in_', VP * 3), ('in_channels', C.c_int * 3), ('in_min', VP), ('in_stats', VP), ('in_gamma', VP),
+                ('in_beta', VP), ('in_count', C.c_double), ('in_act', C.c_int), ('in_slope', C.c_float), ('w_hi', VP),
+                ('w_lo', VP), ('n_pad', C.c_int), ('cout', C.c_int), ('bias', VP), ('bias2', VP), ('out_act', C.c_int),
+                ('residual', VP), ('out', VP), ('out2', VP), ('h', VP), ('z', VP), ('out_stats', VP), ('epilogue', C.c_int),
+                ('B', C.c_int), ('N', C.c_int)]
+
+
 class CorrFeatArgs(C.Structure):
     _fields_ = [('y1', VP), ('y1_stats', VP), ('gn1_gamma', VP), ('gn1_beta', VP), ('prelu1', VP), ('w_out', VP),
                 ('b_out', VP), ('knn_sel', VP), ('moments', VP), ('w_knn', VP), ('b_knn', VP), ('gnk_gamma', VP),
@@ -59,6 +67,8 @@ _SIGNATURES = {
     'pvraft_corr_lookup_fwd': (C.c_int, [VP, VP, VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                          VP, C.c_int, VP, VP, VP, VP, VP]),
     'pvraft_linear_fwd': (C.c_int, [C.POINTER(LinearArgs), VP]),
+    'pvraft_tc_linear_fwd': (C.c_int, [C.POINTER(TcLinearArgs), VP]),
+    'pvraft_tc_weight_split': (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, VP, VP, VP]),
     'pvraft_gn_act_fwd': (C.c_int, [VP, VP, VP, VP, C.c_double, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                     C.c_int, VP, VP]),
     'pvraft_corr_feature_fwd': (C.c_int, [C.POINTER(CorrFeatArgs), VP]),

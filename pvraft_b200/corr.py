@@ -125,11 +125,18 @@ class CorrBlock(nn.Module):
         """coords [B,N,3] -> correlation feature [B,N,64] (point-major).  `motion_args` lets
         UpdateBlock fuse its MotionEncoder into the same launch (see update.py)."""
         b, n, _ = coords.shape
-        lk = self.lookup(coords)
+        nvox = self.num_levels * 27
         stats = ops.new_stats(b, coords.device, 1)
         oc = self.out_conv
-        y1 = ops.linear(lk['vox'], _w(oc[0].weight), _w(oc[0].bias), w_cin=self.num_levels * 27, out_stats=stats[0],
-                        out_act=ACT_NONE)
+        kpad = (nvox + 31) // 32 * 32
+        if ops.tc_supported(n) and kpad - nvox <= 32:
+            # out_conv[0] on tcgen05: the lookup pads the voxel rows to a multiple of 32 channels (zeros)
+            lk = self.lookup(coords, vox_ld=kpad)
+            y1 = ops.tc_linear([lk['vox']], ops.tc_weights(oc[0].weight, cols=nvox, k_pad=kpad), _w(oc[0].bias),
+                               out_stats=stats[0])
+        else:
+            lk = self.lookup(coords)
+            y1 = ops.linear(lk['vox'], _w(oc[0].weight), _w(oc[0].bias), w_cin=nvox, out_stats=stats[0], out_act=ACT_NONE)
         a = self.feature_args(lk, y1, stats[0], b, n)
         corr = torch.empty(b, n, 64, dtype=torch.float32, device=coords.device)
         a.corr_feat = ops._p(corr)

@@ -67,6 +67,7 @@ extern "C" int pvraft_sizeof(int which) {
         case 1: return (int)sizeof(pvraft_corrfeat_args);
         case 2: return (int)sizeof(pvraft_gru_args);
         case 3: return (int)sizeof(pvraft_flowout_args);
+        case 4: return (int)sizeof(pvraft_tc_linear_args);
         default: return -1;
     }
 }

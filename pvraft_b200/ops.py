@@ -5,6 +5,7 @@ hot path happens inside libpvraft_b200.so.  All wrappers require contiguous CUDA
 on anything else -- there is deliberately no CPU / eager fallback.
 """
 import ctypes as C
+import weakref
 
 import torch
 
@@ -72,11 +73,12 @@ def corr_topk(corr, k):
 
 
 def corr_lookup(corr_val, corr_idx, xyz2, coords, levels, base_scale, vox=None, knn_sel=None, moments=None,
-                want_slots=False, want_cube=False):
+                want_slots=False, want_cube=False, vox_ld=None):
     """-> dict(vox [B,N,pad4(levels*27)], knn_sel [B,N,32,4], moments [B,16] f64, [knn_slot], [cube])."""
     b, n, k = corr_val.shape
     dev = corr_val.device
-    vox_ld = (levels * 27 + 3) // 4 * 4          # rows padded to a multiple of 4 floats (zero-filled by the kernel)
+    if vox_ld is None:
+        vox_ld = (levels * 27 + 3) // 4 * 4      # rows padded to a multiple of 4 floats (zero-filled by the kernel)
     if vox is None:
         vox = torch.empty(b, n, vox_ld, dtype=torch.float32, device=dev)
     if knn_sel is None:
@@ -104,6 +106,73 @@ def linear(x, weight, bias=None, *, cin=None, w_ld=0, w_cin=0, in_mode=IN_PLAIN,
                         in_mode, in_act, float(in_slope), _p(weight), int(w_ld), int(w_cin), _p(bias), _p(residual), out_act,
                         _p(out), _p(out_stats, torch.float64), b, n, cin, cout)
     _count(lib().pvraft_linear_fwd(C.byref(a), _stream()), 'linear')
+    return out
+
+
+_TC_WEIGHTS = {}
+TC_PLAIN, TC_GRU_ZR, TC_GRU_Q = 0, 1, 2
+
+
+def tc_weights(weights, col0=0, cols=None, k_pad=None):
+    """tf32 hi/lo split of a (stack of) [cout, cin(,1,1)] weight(s) -> (hi, lo) [n_pad, k_pad], cached per parameter
+    version (inference weights are static, so this runs once)."""
+    if torch.is_tensor(weights):
+        weights = (weights,)
+    # keyed by the identity of the source tensor OBJECTS (validated through weak references and version counters):
+    # a data_ptr key would go stale when the allocator hands a freed weight's address to a new tensor
+    key = tuple(id(w) for w in weights) + (col0, cols, k_pad)
+    hit = _TC_WEIGHTS.get(key)
+    if hit is not None:
+        refs, versions, ptrs, result = hit
+        if all(r() is w and w._version == v and w.data_ptr() == p for r, w, v, p in zip(refs, weights, versions, ptrs)):
+            return result
+    mats = [w.detach().reshape(w.shape[0], -1) for w in weights]
+    ld = mats[0].shape[1]
+    ncols = ld - col0 if cols is None else cols
+    kp = (ncols + 31) // 32 * 32 if k_pad is None else k_pad
+    rows = sum(m.shape[0] for m in mats)
+    n_pad = (rows + 15) // 16 * 16
+    hi = torch.zeros(n_pad, kp, dtype=torch.float32, device=mats[0].device)
+    lo = torch.zeros_like(hi)
+    r0 = 0
+    for m in mats:
+        check(lib().pvraft_tc_weight_split(_p(m.contiguous()), m.shape[0], ncols, ld, col0, m.shape[0], kp,
+                                           hi[r0:].data_ptr(), lo[r0:].data_ptr(), _stream()), 'tc_weight_split')
+        r0 += m.shape[0]
+    if len(_TC_WEIGHTS) > 512:
+        _TC_WEIGHTS.clear()
+    result = (hi, lo, n_pad, rows)
+    _TC_WEIGHTS[key] = (tuple(weakref.ref(w) for w in weights), tuple(w._version for w in weights),
+                        tuple(w.data_ptr() for w in weights), result)
+    return result
+
+
+def tc_supported(n_points, *channels):
+    """The tcgen05 layer needs 128-point tiles that do not straddle samples and 32-channel k-blocks."""
+    return n_points % 128 == 0 and all(c % 32 == 0 for c in channels)
+
+
+def tc_linear(sources, w, bias=None, *, in_min=None, in_stats=None, in_gamma=None, in_beta=None, in_count=0.0,
+              in_act=ACT_NONE, in_slope=0.0, out_act=ACT_NONE, residual=None, out=None, out_stats=None, epilogue=TC_PLAIN,
+              bias2=None, out2=None, h=None, z=None, cout=None):
+    """Fused layer on the tcgen05 tensor cores.  sources: list of [B,N,C_i] tensors concatenated along K;
+    w = (hi, lo, n_pad, rows) from tc_weights()."""
+    hi, lo, n_pad, rows = w
+    b, n, _ = sources[0].shape
+    cout = rows if cout is None else cout
+    if out is None:
+        out = torch.empty(b, n, cout, dtype=torch.float32, device=sources[0].device)
+    a = _lib.TcLinearArgs()
+    for i, src in enumerate(sources):
+        a.in_[i] = _p(src)
+        a.in_channels[i] = src.shape[-1]
+    a.in_min, a.in_stats, a.in_gamma, a.in_beta = _p(in_min), _p(in_stats, torch.float64), _p(in_gamma), _p(in_beta)
+    a.in_count, a.in_act, a.in_slope = float(in_count), in_act, float(in_slope)
+    a.w_hi, a.w_lo, a.n_pad, a.cout = _p(hi), _p(lo), n_pad, cout
+    a.bias, a.bias2, a.out_act, a.residual = _p(bias), _p(bias2), out_act, _p(residual)
+    a.out, a.out2, a.h, a.z = _p(out), _p(out2), _p(h), _p(z)
+    a.out_stats, a.epilogue, a.B, a.N = _p(out_stats, torch.float64), epilogue, b, n
+    _count(lib().pvraft_tc_linear_fwd(C.byref(a), _stream()), 'tc_linear')
     return out
 
 

@@ -60,6 +60,14 @@ class ConvGRU(nn.Module):
         b, n, _ = net.shape
         if out is None:
             out = torch.empty_like(net)
+        if ops.tc_supported(n):
+            # tcgen05: [z|r] = sigmoid(W_zr [h,x]); q = tanh(W_q [r*h, x]); h' = (1-z) h + z q   (update.py:32-39)
+            z, rh = torch.empty_like(net), torch.empty_like(net)
+            ops.tc_linear([net, inp, motion], ops.tc_weights((self.convz.weight, self.convr.weight)), _w(self.convz.bias),
+                          bias2=_w(self.convr.bias), epilogue=ops.TC_GRU_ZR, out=z, out2=rh, h=net, cout=64)
+            ops.tc_linear([rh, inp, motion], ops.tc_weights(self.convq.weight), _w(self.convq.bias), epilogue=ops.TC_GRU_Q,
+                          out=out, h=net, z=z, cout=64)
+            return out
         a = _lib.GruArgs(ops._p(net), ops._p(inp), ops._p(motion), ops._p(_w(self.convz.weight)), ops._p(_w(self.convz.bias)),
                          ops._p(_w(self.convr.weight)), ops._p(_w(self.convr.bias)), ops._p(_w(self.convq.weight)),
                          ops._p(_w(self.convq.bias)), ops._p(out), b, n)

@@ -355,3 +355,49 @@ def test_corr_matmul_tcgen05(dev, b, n, c):
     # and against the reference's own fp32 formulation (model/corr.py:95-100)
     ref32 = O.calculate_corr(f1.transpose(1, 2), f2.transpose(1, 2))
     assert rel_err(got, ref32) < 5e-6
+
+
+@pytest.mark.parametrize('b,n,cin,cout,mode', [(2, 256, 64, 64, 'plain'), (1, 1024, 96, 128, 'gn'), (2, 128, 64, 64, 'minmax'),
+                                               (1, 256, 32, 48, 'plain'), (1, 384, 128, 3, 'gn')])
+def test_tc_linear_matches_fp64(dev, b, n, cin, cout, mode):
+    """tcgen05 3xTF32 layer (prologue + epilogue) against an fp64 evaluation and against the CUDA-core kernel."""
+    from pvraft_b200 import ops
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    x = torch.randn(b, n, cin, generator=g) * 1.5 + 0.2
+    xmin = x - torch.rand(b, n, cin, generator=g)
+    w = torch.randn(cout, cin, generator=g) / cin ** 0.5
+    bias = torch.randn(cout, generator=g)
+    res = torch.randn(b, n, cout, generator=g)
+    gamma, beta = torch.randn(cin, generator=g), torch.randn(cin, generator=g) * 0.1
+    xd, wd = x.double(), w.double()
+    kw = {}
+    if mode == 'plain':
+        a_in = xd
+    else:
+        stats = torch.stack([xd.reshape(b, n, 8, cin // 8).sum((1, 3)), (xd ** 2).reshape(b, n, 8, cin // 8).sum((1, 3))], -1)
+        cnt = float(n * cin // 8)
+        mean = stats[..., 0] / cnt
+        rstd = (stats[..., 1] / cnt - mean ** 2 + 1e-5).rsqrt()
+        sc = (rstd.repeat_interleave(cin // 8, 1) * gamma.double()).unsqueeze(1)
+        sh = beta.double() - mean.repeat_interleave(cin // 8, 1).unsqueeze(1) * sc
+        raw = torch.where(sc < 0, xmin.double(), xd) if mode == 'minmax' else xd
+        t = raw * sc + sh
+        a_in = torch.where(t >= 0, t, 0.1 * t)
+        kw = dict(in_stats=stats.to(dev), in_gamma=gamma.to(dev), in_beta=beta.to(dev), in_count=cnt, in_act=ops.ACT_LRELU, in_slope=0.1)
+        if mode == 'minmax':
+            kw['in_min'] = xmin.to(dev)
+    want = torch.relu(a_in @ wd.t() + bias.double()) + res.double()
+    ostats = torch.zeros(b, 8, 2, dtype=torch.float64, device=dev) if cout % 32 == 0 else None
+    got = ops.tc_linear([x.to(dev)], ops.tc_weights(w.to(dev)), bias.to(dev), out_act=ops.ACT_RELU, residual=res.to(dev),
+                        out_stats=ostats, **kw)
+    err = float((got.cpu().double() - want).abs().max() / want.abs().max())
+    assert err < 3e-6, err
+    if ostats is not None:
+        s1 = want.reshape(b, n, 8, cout // 8).sum((1, 3))
+        s2 = (want ** 2).reshape(b, n, 8, cout // 8).sum((1, 3))
+        assert torch.allclose(ostats[..., 0].cpu(), s1, rtol=1e-5, atol=1e-3)
+        assert torch.allclose(ostats[..., 1].cpu(), s2, rtol=1e-5, atol=1e-3)
+    ref_mode = {'plain': ops.IN_PLAIN, 'gn': ops.IN_GN, 'minmax': ops.IN_GN_MINMAX}[mode]
+    kw2 = {k: v for k, v in kw.items()}
+    ref = ops.linear(x.to(dev), w.to(dev), bias.to(dev), in_mode=ref_mode, out_act=ops.ACT_RELU, residual=res.to(dev), **kw2)
+    assert rel_err(got.cpu(), ref.cpu()) < 5e-6
