@@ -186,6 +186,7 @@ k_corr_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             }
         }
     }
+    __syncwarp();   // the producer / MMA roles run on one lane: re-converge before the CTA-wide (aligned) barrier
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {

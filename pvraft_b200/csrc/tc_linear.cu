@@ -21,10 +21,13 @@
 
 namespace pvraft {
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 448;   // weight TMA | MMA | 8 load+transform warps | 4 epilogue warps
 constexpr int kTcM = 128, kTcKB = 32;
 constexpr int kTcABytes = kTcM * kTcKB * 4;   // 16 KB: one activation box
-constexpr int kTcMaxStages = 4;
+constexpr int kTcMaxStages = 6;
+
+__device__ unsigned long long g_tc_clock[64];   // debug timeline of CTA 0 (env PVRAFT_TC_DBG=1)
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 enum TcEpilogue { TC_EPI_PLAIN = 0, TC_EPI_GRU_ZR = 1, TC_EPI_GRU_Q = 2 };
 
@@ -49,8 +52,12 @@ struct TcParams {
     const float* z;           // GRU_Q: update gate [M,64]
     double* out_stats;        // [B,8,2] or null
     int M, N, K, cout, pts_per_sample;
+    const float* src[3];      // activation sources [M, 32*seg_kb[i]] row-major
+    const float* src_min;     // per-channel minima paired with src[0] (minmax prologue)
     int seg_kb[3];            // k-blocks contributed by each activation source
-    int stages;               // depth of the shared-memory ring (1..4), chosen by the host for occupancy
+    int stages;               // depth of the shared-memory ring (1..4)
+    int w_resident;           // 1: all weight boxes are loaded once per CTA and stay in shared memory
+    int dbg;                  // 1: CTA 0 records a globaltimer timeline into g_tc_clock
 };
 
 __device__ __forceinline__ unsigned tsu32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -99,10 +106,10 @@ __device__ __forceinline__ void tumma_tf32(unsigned tmem_d, unsigned long long d
 __device__ __forceinline__ void tumma_commit(void* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tsu32(bar)) : "memory");
 }
+// round-to-nearest (ties away from zero) to the 10-bit TF32 mantissa with two full-rate integer ops; identical to
+// cvt.rna.tf32.f32 for finite values (the conversion instruction runs at a fraction of the ALU rate)
 __device__ __forceinline__ float tf32_rna(float x) {
-    unsigned r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&v)[32]) {
     asm volatile(
@@ -117,48 +124,215 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&v)[32]) {
 }
 __device__ __forceinline__ float tsigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
-__global__ void __launch_bounds__(kTcThreads, 3)
-k_tc_linear(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-            const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_amin,
-            const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams p) {
+// epilogue of one accumulator buffer: thread = point (TMEM lane)
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, int quad, int lane, int row0, int sample,
+                                            const float* __restrict__ s_bias, float* __restrict__ s_stage, float* __restrict__ s_part) {
+    const int row = row0 + quad * 32 + lane;
+    const bool live = row < p.M;
+    const int gsz = p.cout / PVRAFT_GN_GROUPS;
+    const unsigned tl = tacc + ((unsigned)(quad * 32) << 16);
+    if (p.epi == TC_EPI_PLAIN) {
+        const bool vec = (p.cout & 3) == 0;
+        float* stg = s_stage + (size_t)quad * 32 * 36;   // this warp's [32 rows][36] staging tile
+        const bool clk = p.dbg && blockIdx.x == 0 && quad == 0 && lane == 0 && row0 == 0;
+        for (int c0 = 0; c0 < p.N; c0 += 32) {
+            unsigned v[32];
+            if (clk) g_tc_clock[32 + (c0 >> 5) * 4] = gtimer();
+            tmem_ld32(tl + (unsigned)c0, v);
+            if (clk) g_tc_clock[33 + (c0 >> 5) * 4] = gtimer();
+            float y[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0 + q * 4);
+                y[q * 4 + 0] = apply_act(__uint_as_float(v[q * 4 + 0]) + bv.x, p.out_act, 0.f);
+                y[q * 4 + 1] = apply_act(__uint_as_float(v[q * 4 + 1]) + bv.y, p.out_act, 0.f);
+                y[q * 4 + 2] = apply_act(__uint_as_float(v[q * 4 + 2]) + bv.z, p.out_act, 0.f);
+                y[q * 4 + 3] = apply_act(__uint_as_float(v[q * 4 + 3]) + bv.w, p.out_act, 0.f);
+            }
+            if (p.residual != nullptr && live) {   // (rare: FlotRefine.fc) thread-per-row loads, before the statistics
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c0 + i < p.cout) y[i] += __ldg(p.residual + (size_t)row * p.cout + c0 + i);
+            }
+            if (vec) {
+                // transpose through shared memory so that a store instruction writes 4 rows x 128 contiguous bytes
+                // (thread-per-row stores would scatter 32 half-filled sectors per instruction)
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4*>(stg + lane * 36 + q * 4) = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+                __syncwarp();
+                if (clk) g_tc_clock[34 + (c0 >> 5) * 4] = gtimer();
+                const int cq = lane & 7, rsub = lane >> 3;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = i * 4 + rsub;
+                    const int grow = row0 + quad * 32 + r;
+                    const int c = c0 + cq * 4;
+                    if (grow < p.M && c < p.cout) {
+                        *reinterpret_cast<float4*>(p.out + (size_t)grow * p.cout + c) = *reinterpret_cast<const float4*>(stg + r * 36 + cq * 4);
+                    }
+                }
+                if (clk) g_tc_clock[35 + (c0 >> 5) * 4] = gtimer();
+            } else if (live) {
+                float* o = p.out + (size_t)row * p.cout + c0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (c0 + i < p.cout) o[i] = y[i];
+                }
+            }
+            if (p.out_stats != nullptr) {
+                // 8 partial (sum, sum^2) pairs per thread: sub-group j covers columns [4j, 4j+4) of this step; every
+                // GroupNorm group is a union of whole sub-groups (group size is a multiple of 4)
+                float s1[8], s2[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    s1[j] = 0.f; s2[j] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float a = live ? y[j * 4 + i] : 0.f;
+                        s1[j] += a;
+                        s2[j] = fmaf(a, a, s2[j]);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        s1[j] += __shfl_xor_sync(kFull, s1[j], o);
+                        s2[j] += __shfl_xor_sync(kFull, s2[j], o);
+                    }
+                }
+                if (lane < 8) {   // lane j parks sub-group j of this warp; the 4 warps are combined below
+                    float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { a1 = lane == j ? s1[j] : a1; a2 = lane == j ? s2[j] : a2; }
+                    s_part[(quad * 32 + (c0 >> 2) + lane) * 2 + 0] = a1;
+                    s_part[(quad * 32 + (c0 >> 2) + lane) * 2 + 1] = a2;
+                }
+            }
+        }
+        if (p.out_stats != nullptr) {
+            // combine the 4 epilogue warps: one double atomic per (sub-group, moment) and tile instead of four
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            const int t = quad * 32 + lane;   // 0..127
+            const int nsub = p.N >> 2;        // sub-groups of 4 columns
+            if (t < nsub * 2) {
+                const int sg = t >> 1, m = t & 1;
+                const double tot = (double)s_part[(0 * 32 + sg) * 2 + m] + (double)s_part[(1 * 32 + sg) * 2 + m] +
+                                   (double)s_part[(2 * 32 + sg) * 2 + m] + (double)s_part[(3 * 32 + sg) * 2 + m];
+                const int c = sg * 4;
+                if (c < p.cout) atomicAdd(p.out_stats + (size_t)sample * 16 + (c / gsz) * 2 + m, tot);
+            }
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+    } else if (p.epi == TC_EPI_GRU_ZR) {
+        // accumulator columns 0..63 = z pre-activation, 64..127 = r pre-activation (model/update.py:34-35)
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+            unsigned vz[32], vr[32];
+            tmem_ld32(tl + (unsigned)c0, vz);
+            tmem_ld32(tl + (unsigned)(64 + c0), vr);
+            if (live) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int c = c0 + q * 4;
+                    const float4 hv = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)row * 64 + c));
+                    const float4 bz = *reinterpret_cast<const float4*>(s_bias + c);
+                    const float4 br = *reinterpret_cast<const float4*>(s_bias + p.N + c);
+                    float4 z, rh;
+                    z.x = tsigmoid(__uint_as_float(vz[q * 4 + 0]) + bz.x); z.y = tsigmoid(__uint_as_float(vz[q * 4 + 1]) + bz.y);
+                    z.z = tsigmoid(__uint_as_float(vz[q * 4 + 2]) + bz.z); z.w = tsigmoid(__uint_as_float(vz[q * 4 + 3]) + bz.w);
+                    rh.x = tsigmoid(__uint_as_float(vr[q * 4 + 0]) + br.x) * hv.x; rh.y = tsigmoid(__uint_as_float(vr[q * 4 + 1]) + br.y) * hv.y;
+                    rh.z = tsigmoid(__uint_as_float(vr[q * 4 + 2]) + br.z) * hv.z; rh.w = tsigmoid(__uint_as_float(vr[q * 4 + 3]) + br.w) * hv.w;
+                    *reinterpret_cast<float4*>(p.out + (size_t)row * 64 + c) = z;
+                    *reinterpret_cast<float4*>(p.out2 + (size_t)row * 64 + c) = rh;
+                }
+            }
+        }
+    } else {
+        // q = tanh(acc + b); h' = (1 - z) h + z q   (model/update.py:37-39)
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+            unsigned vq[32];
+            tmem_ld32(tl + (unsigned)c0, vq);
+            if (live) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int c = c0 + q * 4;
+                    const float4 hv = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)row * 64 + c));
+                    const float4 zv = __ldg(reinterpret_cast<const float4*>(p.z + (size_t)row * 64 + c));
+                    const float4 bq = *reinterpret_cast<const float4*>(s_bias + c);
+                    float4 o;
+                    o.x = (1.f - zv.x) * hv.x + zv.x * tanhf(__uint_as_float(vq[q * 4 + 0]) + bq.x);
+                    o.y = (1.f - zv.y) * hv.y + zv.y * tanhf(__uint_as_float(vq[q * 4 + 1]) + bq.y);
+                    o.z = (1.f - zv.z) * hv.z + zv.z * tanhf(__uint_as_float(vq[q * 4 + 2]) + bq.z);
+                    o.w = (1.f - zv.w) * hv.w + zv.w * tanhf(__uint_as_float(vq[q * 4 + 3]) + bq.w);
+                    *reinterpret_cast<float4*>(p.out + (size_t)row * 64 + c) = o;
+                }
+            }
+        }
+    }
+}
+
+// Persistent, warp-specialised kernel:
+//   warp 0       weight producer (TMA boxes: once per CTA when the hi/lo weights fit in shared memory, else per k-block)
+//   warp 1       MMA issuer (one lane)
+//   warps 2-9    activation loaders + transform: coalesced 128-bit global loads of the raw fp32 rows (a 2-D TMA box of
+//                128-byte rows is served at ~1 us per 16 KB by the per-SM TMA unit, measured; plain LDG is ~8x faster),
+//                GroupNorm affine + activation, hi/lo split, stores at the SWIZZLE_128B offsets of the operand tiles;
+//                the loads of k-block i+1 are in flight while k-block i is transformed (double-buffered registers)
+//   warps 10-13  epilogue, one TMEM accumulator buffer behind the MMA
+// A CTA walks tiles blockIdx.x, +gridDim.x, ...; the operand ring and the two accumulators run across tile boundaries.
+constexpr int kTcXform = 256;   // transform threads
+
+struct XformRegs {
+    float4 a[4], m[4];
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    // stage layout: [A hi (raw in, hi out) 16K][A lo 16K][W hi N*128][W lo N*128][A min raw 16K, only with minmax]
+    // stage layout: [A hi 16K][A lo 16K][W hi N*128][W lo N*128, only when the weights are streamed];
+    // resident weights live behind the ring as num_kb x [W hi][W lo]
     const int w_bytes = p.N * kTcKB * 4;
-    const int w_off = 2 * kTcABytes, min_off = 2 * kTcABytes + 2 * w_bytes;
-    const int stage_bytes = (p.minmax ? 3 : 2) * kTcABytes + 2 * w_bytes;
-    const int kTcStages = p.stages;
-    float* s_scale = reinterpret_cast<float*>(tiles + (size_t)kTcStages * stage_bytes);   // [K]
+    const int w_off = 2 * kTcABytes;
+    const int stage_bytes = w_off + (p.w_resident ? 0 : 2 * w_bytes);
+    const int S = p.stages;
+    const int num_kb = p.K / kTcKB;
+    unsigned char* w_res = tiles + (size_t)S * stage_bytes;
+    float* s_scale = reinterpret_cast<float*>(w_res + (p.w_resident ? (size_t)num_kb * 2 * w_bytes : 0));   // [K]
     float* s_shift = s_scale + p.K;
-    float* s_bias = s_shift + p.K;                                                        // [2 * N]
-    __shared__ __align__(8) unsigned long long s_full[kTcMaxStages], s_ready[kTcMaxStages], s_empty[kTcMaxStages], s_tmem_full;
+    float* s_bias = s_shift + p.K;                                                // [2 * N]
+    float* s_estage = s_bias + 2 * p.N;                                           // [4 warps][32][36] epilogue staging
+    float* s_part = s_estage + 4 * 32 * 36;                                       // [4 warps][32 sub-groups][2]
+    __shared__ __align__(8) unsigned long long s_full[kTcMaxStages], s_ready[kTcMaxStages], s_empty[kTcMaxStages];
+    __shared__ __align__(8) unsigned long long s_acc_full[2], s_acc_empty[2], s_w_full;
     __shared__ unsigned s_tmem_base;
     const int warp = warp_id(), lane = lane_id();
-    const int tile = blockIdx.x;
-    const int row0 = tile * kTcM;
-    const int sample = row0 / p.pts_per_sample;
-    const int num_kb = p.K / kTcKB;
-    const unsigned tmem_cols = p.N <= 32 ? 32u : p.N <= 64 ? 64u : p.N <= 128 ? 128u : 256u;
+    const int n_tiles = (p.M + kTcM - 1) / kTcM;
+    const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int total_steps = my_tiles * num_kb;
+    const unsigned acc_cols = p.N <= 32 ? 32u : p.N <= 64 ? 64u : 128u;   // columns per accumulator buffer
+    const unsigned tmem_cols = acc_cols * 2;
+    const bool clk = p.dbg && blockIdx.x == 0;
+    if (clk && threadIdx.x == 0) g_tc_clock[0] = gtimer();
 
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_lo) : "memory");
+    }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kTcStages; ++s) { tmbar_init(&s_full[s], 1); tmbar_init(&s_ready[s], 128); tmbar_init(&s_empty[s], 1); }
-        tmbar_init(&s_tmem_full, 1);
+        for (int s = 0; s < S; ++s) { tmbar_init(&s_full[s], 1); tmbar_init(&s_ready[s], kTcXform); tmbar_init(&s_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { tmbar_init(&s_acc_full[a], 1); tmbar_init(&s_acc_empty[a], 128); }
+        tmbar_init(&s_w_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tsu32(&s_tmem_base)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp >= 2 && p.in_stats != nullptr) {   // folded GroupNorm affine of every input channel of this sample
-        const int gsz = p.K / PVRAFT_GN_GROUPS;
-        for (int k = threadIdx.x - 64; k < p.K; k += 128) {
-            const GnAffine af = gn_affine(p.in_stats + (size_t)sample * 16 + (k / gsz) * 2, p.in_count, __ldg(p.in_gamma + k), __ldg(p.in_beta + k));
-            s_scale[k] = af.scale;
-            s_shift[k] = af.shift;
-        }
-    }
-    if (warp >= 2) {
-        for (int c = threadIdx.x - 64; c < p.N; c += 128) {
+    if (warp >= 10) {
+        for (int c = threadIdx.x - 320; c < p.N; c += 128) {
             s_bias[c] = (p.bias != nullptr && c < p.cout) ? __ldg(p.bias + c) : 0.f;
             s_bias[p.N + c] = (p.bias2 != nullptr && c < p.cout) ? __ldg(p.bias2 + c) : 0.f;
         }
@@ -169,67 +343,116 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
     const unsigned tmem = s_tmem_base;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== weight producer =====
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kTcStages;
-                const unsigned phase = (unsigned)(kb / kTcStages) & 1u;
-                tmbar_wait(&s_empty[s], phase ^ 1u);
-                unsigned char* st = tiles + (size_t)s * stage_bytes;
-                tmbar_expect_tx(&s_full[s], (unsigned)(kTcABytes * (p.minmax ? 2 : 1) + 2 * w_bytes));
-                // which source tensor does this k-block come from?
-                int seg = 0, kk = kb;
-                if (kk >= p.seg_kb[0]) { kk -= p.seg_kb[0]; seg = 1; if (kk >= p.seg_kb[1]) { kk -= p.seg_kb[1]; seg = 2; } }
-                const CUtensorMap* ma = seg == 0 ? &map_a0 : seg == 1 ? &map_a1 : &map_a2;
-                ttma_load_2d(st, ma, &s_full[s], kk * kTcKB, row0);
-                if (p.minmax) ttma_load_2d(st + min_off, &map_amin, &s_full[s], kk * kTcKB, row0);
-                ttma_load_2d(st + w_off, &map_w_hi, &s_full[s], kb * kTcKB, 0);
-                ttma_load_2d(st + w_off + w_bytes, &map_w_lo, &s_full[s], kb * kTcKB, 0);
+            if (p.w_resident) {   // the whole weight matrix (hi and lo) once per CTA
+                tmbar_expect_tx(&s_w_full, (unsigned)(num_kb * 2 * w_bytes));
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ttma_load_2d(w_res + (size_t)kb * 2 * w_bytes, &map_w_hi, &s_w_full, kb * kTcKB, 0);
+                    ttma_load_2d(w_res + (size_t)kb * 2 * w_bytes + w_bytes, &map_w_lo, &s_w_full, kb * kTcKB, 0);
+                }
+            } else {
+                for (int step = 0; step < total_steps; ++step) {
+                    const int s = step % S, kb = step % num_kb;
+                    const unsigned phase = (unsigned)(step / S) & 1u;
+                    tmbar_wait(&s_empty[s], phase ^ 1u);
+                    unsigned char* st = tiles + (size_t)s * stage_bytes;
+                    tmbar_expect_tx(&s_full[s], (unsigned)(2 * w_bytes));
+                    ttma_load_2d(st + w_off, &map_w_hi, &s_full[s], kb * kTcKB, 0);
+                    ttma_load_2d(st + w_off + w_bytes, &map_w_lo, &s_full[s], kb * kTcKB, 0);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(p.N >> 3) << 17) | ((unsigned)(kTcM >> 4) << 24);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kTcStages;
-                const unsigned phase = (unsigned)(kb / kTcStages) & 1u;
-                tmbar_wait(&s_ready[s], phase);   // transformed activations (and, transitively, the TMA data) are in place
+            if (p.w_resident) tmbar_wait(&s_w_full, 0u);
+            int step = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int acc = ti & 1;
+                const unsigned acc_phase = (unsigned)(ti >> 1) & 1u;
+                tmbar_wait(&s_acc_empty[acc], acc_phase ^ 1u);   // the epilogue has drained this accumulator buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                unsigned char* st = tiles + (size_t)s * stage_bytes;
-                const unsigned long long a_hi = tumma_desc(st), a_lo = tumma_desc(st + kTcABytes);
-                const unsigned long long b_hi = tumma_desc(st + w_off), b_lo = tumma_desc(st + w_off + w_bytes);
+                const unsigned tacc = tmem + (unsigned)acc * acc_cols;
+                for (int kb = 0; kb < num_kb; ++kb, ++step) {
+                    const int s = step % S;
+                    const unsigned phase = (unsigned)(step / S) & 1u;
+                    tmbar_wait(&s_ready[s], phase);               // transformed activations are in place
+                    if (!p.w_resident) tmbar_wait(&s_full[s], phase);   // streamed weight boxes have landed
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    unsigned char* st = tiles + (size_t)s * stage_bytes;
+                    const unsigned long long a_hi = tumma_desc(st), a_lo = tumma_desc(st + kTcABytes);
+                    const unsigned char* wb = p.w_resident ? w_res + (size_t)kb * 2 * w_bytes : st + w_off;
+                    const unsigned long long b_hi = tumma_desc(wb), b_lo = tumma_desc(wb + w_bytes);
 #pragma unroll
-                for (int k = 0; k < kTcKB / 8; ++k) {
-                    const unsigned long long off = (unsigned long long)(k * 2);
-                    tumma_tf32(tmem, a_hi + off, b_hi + off, idesc, (kb | k) != 0 ? 1u : 0u);
-                    tumma_tf32(tmem, a_lo + off, b_hi + off, idesc, 1u);
-                    tumma_tf32(tmem, a_hi + off, b_lo + off, idesc, 1u);
+                    for (int k = 0; k < kTcKB / 8; ++k) {
+                        const unsigned long long off = (unsigned long long)(k * 2);
+                        tumma_tf32(tacc, a_hi + off, b_hi + off, idesc, (kb | k) != 0 ? 1u : 0u);
+                        tumma_tf32(tacc, a_lo + off, b_hi + off, idesc, 1u);
+                        tumma_tf32(tacc, a_hi + off, b_lo + off, idesc, 1u);
+                    }
+                    tumma_commit(&s_empty[s]);
+                    if (clk && step < 8) g_tc_clock[16 + step] = gtimer();
                 }
-                tumma_commit(&s_empty[s]);
-                if (kb == num_kb - 1) tumma_commit(&s_tmem_full);
+                tumma_commit(&s_acc_full[acc]);
             }
         }
-    } else {
-        // ===== transform (prologue + hi/lo split), then epilogue =====
-        const int t = threadIdx.x - 64;   // 0..127
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % kTcStages;
-            const unsigned phase = (unsigned)(kb / kTcStages) & 1u;
-            tmbar_wait(&s_full[s], phase);
+    } else if (warp < 10) {
+        // ===== activation loaders + transform =====
+        const int t = threadIdx.x - 64;   // 0..255: chunk c = t + 256*i, i < 4, of the 1024 16-byte chunks of a k-block
+        int cur_sample = -1;
+        auto issue = [&](XformRegs& R, int step) {
+            const int ti = step / num_kb, kb = step - ti * num_kb;
+            const int row0 = (blockIdx.x + ti * gridDim.x) * kTcM;
+            int seg = 0, kk = kb;   // which source tensor does this k-block come from?
+            if (kk >= p.seg_kb[0]) { kk -= p.seg_kb[0]; seg = 1; if (kk >= p.seg_kb[1]) { kk -= p.seg_kb[1]; seg = 2; } }
+            const float* src = p.src[seg];
+            const int ld = p.seg_kb[seg] * kTcKB;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = t + i * kTcXform, r = c >> 3, lc = c & 7;
+                const long long grow = (long long)row0 + r;
+                R.a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                R.m[i] = R.a[i];
+                if (grow < p.M) {
+                    const size_t off = (size_t)grow * ld + kk * kTcKB + lc * 4;
+                    R.a[i] = __ldg(reinterpret_cast<const float4*>(src + off));
+                    if (p.minmax) R.m[i] = __ldg(reinterpret_cast<const float4*>(p.src_min + off));
+                }
+            }
+        };
+        auto process = [&](const XformRegs& R, int step) {
+            const int ti = step / num_kb, kb = step - ti * num_kb;
+            const int s = step % S;
+            const unsigned phase = (unsigned)(step / S) & 1u;
+            if (p.in_stats != nullptr && kb == 0) {
+                const int sample = ((blockIdx.x + ti * gridDim.x) * kTcM) / p.pts_per_sample;
+                if (sample != cur_sample) {   // folded GroupNorm affine of every input channel of this sample
+                    asm volatile("bar.sync 1, 256;" ::: "memory");   // everyone is done with the previous sample's table
+                    const int gsz = p.K / PVRAFT_GN_GROUPS;
+                    for (int k = t; k < p.K; k += kTcXform) {
+                        const GnAffine af = gn_affine(p.in_stats + (size_t)sample * 16 + (k / gsz) * 2, p.in_count, __ldg(p.in_gamma + k), __ldg(p.in_beta + k));
+                        s_scale[k] = af.scale;
+                        s_shift[k] = af.shift;
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    cur_sample = sample;
+                }
+            }
+            tmbar_wait(&s_empty[s], phase ^ 1u);   // the MMAs that read this stage last time have retired
             unsigned char* st = tiles + (size_t)s * stage_bytes;
-#pragma unroll 2
-            for (int c = t; c < kTcABytes / 16; c += 128) {
-                float4 x = *reinterpret_cast<const float4*>(st + (size_t)c * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = t + i * kTcXform, r = c >> 3, lc = c & 7;
+                float4 x = R.a[i];
                 if (p.in_stats != nullptr) {
-                    const int r = c >> 3, lc = (c & 7) ^ (r & 7);      // logical 16-byte chunk of row r under SWIZZLE_128B
                     const int k = kb * kTcKB + lc * 4;
                     const float4 sc = *reinterpret_cast<const float4*>(s_scale + k);
                     const float4 sh = *reinterpret_cast<const float4*>(s_shift + k);
                     if (p.minmax) {
-                        const float4 mn = *reinterpret_cast<const float4*>(st + min_off + (size_t)c * 16);
-                        x.x = sc.x < 0.f ? mn.x : x.x; x.y = sc.y < 0.f ? mn.y : x.y;
-                        x.z = sc.z < 0.f ? mn.z : x.z; x.w = sc.w < 0.f ? mn.w : x.w;
+                        x.x = sc.x < 0.f ? R.m[i].x : x.x; x.y = sc.y < 0.f ? R.m[i].y : x.y;
+                        x.z = sc.z < 0.f ? R.m[i].z : x.z; x.w = sc.w < 0.f ? R.m[i].w : x.w;
                     }
                     x.x = apply_act(fmaf(x.x, sc.x, sh.x), p.in_act, p.in_slope);
                     x.y = apply_act(fmaf(x.y, sc.y, sh.y), p.in_act, p.in_slope);
@@ -239,142 +462,46 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ 
                 float4 hi, lo;
                 hi.x = tf32_rna(x.x); hi.y = tf32_rna(x.y); hi.z = tf32_rna(x.z); hi.w = tf32_rna(x.w);
                 lo.x = tf32_rna(x.x - hi.x); lo.y = tf32_rna(x.y - hi.y); lo.z = tf32_rna(x.z - hi.z); lo.w = tf32_rna(x.w - hi.w);
-                *reinterpret_cast<float4*>(st + (size_t)c * 16) = hi;
-                *reinterpret_cast<float4*>(st + kTcABytes + (size_t)c * 16) = lo;
+                // K-major SWIZZLE_128B: 16-byte chunk lc of row r lives at chunk (lc ^ (r & 7)) of the row's 128 bytes
+                const int off = r * 128 + ((lc ^ (r & 7)) << 4);
+                *reinterpret_cast<float4*>(st + off) = hi;
+                *reinterpret_cast<float4*>(st + kTcABytes + off) = lo;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
             tmbar_arrive(&s_ready[s]);
+            if (clk && t == 0 && step < 8) g_tc_clock[8 + step] = gtimer();
+        };
+        XformRegs RA, RB;
+        if (total_steps > 0) issue(RA, 0);
+        for (int step = 0; step < total_steps; step += 2) {
+            if (step + 1 < total_steps) issue(RB, step + 1);
+            process(RA, step);
+            if (step + 2 < total_steps) issue(RA, step + 2);
+            if (step + 1 < total_steps) process(RB, step + 1);
         }
-        // ---- epilogue: thread = point (TMEM lane) ----
-        tmbar_wait(&s_tmem_full, 0u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int quad = warp & 3;
-        const int row = row0 + quad * 32 + lane;
-        const bool live = row < p.M;
-        const int gsz = p.cout / PVRAFT_GN_GROUPS;
-        if (p.epi == TC_EPI_PLAIN) {
-            const bool vec = (p.cout & 3) == 0;
-            for (int c0 = 0; c0 < p.N; c0 += 32) {
-                unsigned v[32];
-                tmem_ld32(tmem + ((unsigned)(quad * 32) << 16) + (unsigned)c0, v);
-                float y[32];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0 + q * 4);
-                    y[q * 4 + 0] = apply_act(__uint_as_float(v[q * 4 + 0]) + bv.x, p.out_act, 0.f);
-                    y[q * 4 + 1] = apply_act(__uint_as_float(v[q * 4 + 1]) + bv.y, p.out_act, 0.f);
-                    y[q * 4 + 2] = apply_act(__uint_as_float(v[q * 4 + 2]) + bv.z, p.out_act, 0.f);
-                    y[q * 4 + 3] = apply_act(__uint_as_float(v[q * 4 + 3]) + bv.w, p.out_act, 0.f);
-                }
-                if (live) {
-                    float* o = p.out + (size_t)row * p.cout + c0;
-                    if (vec) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            if (c0 + q * 4 < p.cout) {
-                                if (p.residual != nullptr) {
-                                    const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * p.cout + c0 + q * 4));
-                                    y[q * 4] += rv.x; y[q * 4 + 1] += rv.y; y[q * 4 + 2] += rv.z; y[q * 4 + 3] += rv.w;
-                                }
-                                *reinterpret_cast<float4*>(o + q * 4) = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if (c0 + i < p.cout) {
-                                if (p.residual != nullptr) y[i] += __ldg(p.residual + (size_t)row * p.cout + c0 + i);
-                                o[i] = y[i];
-                            }
-                        }
-                    }
-                }
-                if (p.out_stats != nullptr) {
-                    // 8 partial (sum, sum^2) pairs per thread: sub-group j covers columns [4j, 4j+4) of this step; every
-                    // GroupNorm group is a union of whole sub-groups (group size is a multiple of 4)
-                    float s1[8], s2[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        s1[j] = 0.f; s2[j] = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float a = live ? y[j * 4 + i] : 0.f;
-                            s1[j] += a;
-                            s2[j] = fmaf(a, a, s2[j]);
-                        }
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            s1[j] += __shfl_xor_sync(kFull, s1[j], o);
-                            s2[j] += __shfl_xor_sync(kFull, s2[j], o);
-                        }
-                    }
-                    if (lane < 8) {   // lane j publishes sub-group j
-                        float a1 = 0.f, a2 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { a1 = lane == j ? s1[j] : a1; a2 = lane == j ? s2[j] : a2; }
-                        const int c = c0 + lane * 4;
-                        if (c < p.cout) {
-                            const int grp = c / gsz;
-                            atomicAdd(p.out_stats + (size_t)sample * 16 + grp * 2 + 0, (double)a1);
-                            atomicAdd(p.out_stats + (size_t)sample * 16 + grp * 2 + 1, (double)a2);
-                        }
-                    }
-                }
-            }
-        } else if (p.epi == TC_EPI_GRU_ZR) {
-            // accumulator columns 0..63 = z pre-activation, 64..127 = r pre-activation (model/update.py:34-35)
-            for (int c0 = 0; c0 < 64; c0 += 32) {
-                unsigned vz[32], vr[32];
-                tmem_ld32(tmem + ((unsigned)(quad * 32) << 16) + (unsigned)c0, vz);
-                tmem_ld32(tmem + ((unsigned)(quad * 32) << 16) + (unsigned)(64 + c0), vr);
-                if (live) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int c = c0 + q * 4;
-                        const float4 hv = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)row * 64 + c));
-                        const float4 bz = *reinterpret_cast<const float4*>(s_bias + c);
-                        const float4 br = *reinterpret_cast<const float4*>(s_bias + p.N + c);
-                        float4 z, rh;
-                        z.x = tsigmoid(__uint_as_float(vz[q * 4 + 0]) + bz.x); z.y = tsigmoid(__uint_as_float(vz[q * 4 + 1]) + bz.y);
-                        z.z = tsigmoid(__uint_as_float(vz[q * 4 + 2]) + bz.z); z.w = tsigmoid(__uint_as_float(vz[q * 4 + 3]) + bz.w);
-                        rh.x = tsigmoid(__uint_as_float(vr[q * 4 + 0]) + br.x) * hv.x; rh.y = tsigmoid(__uint_as_float(vr[q * 4 + 1]) + br.y) * hv.y;
-                        rh.z = tsigmoid(__uint_as_float(vr[q * 4 + 2]) + br.z) * hv.z; rh.w = tsigmoid(__uint_as_float(vr[q * 4 + 3]) + br.w) * hv.w;
-                        *reinterpret_cast<float4*>(p.out + (size_t)row * 64 + c) = z;
-                        *reinterpret_cast<float4*>(p.out2 + (size_t)row * 64 + c) = rh;
-                    }
-                }
-            }
-        } else {
-            // q = tanh(acc + b); h' = (1 - z) h + z q   (model/update.py:37-39)
-            for (int c0 = 0; c0 < 64; c0 += 32) {
-                unsigned vq[32];
-                tmem_ld32(tmem + ((unsigned)(quad * 32) << 16) + (unsigned)c0, vq);
-                if (live) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int c = c0 + q * 4;
-                        const float4 hv = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)row * 64 + c));
-                        const float4 zv = __ldg(reinterpret_cast<const float4*>(p.z + (size_t)row * 64 + c));
-                        const float4 bq = *reinterpret_cast<const float4*>(s_bias + c);
-                        float4 o;
-                        o.x = (1.f - zv.x) * hv.x + zv.x * tanhf(__uint_as_float(vq[q * 4 + 0]) + bq.x);
-                        o.y = (1.f - zv.y) * hv.y + zv.y * tanhf(__uint_as_float(vq[q * 4 + 1]) + bq.y);
-                        o.z = (1.f - zv.z) * hv.z + zv.z * tanhf(__uint_as_float(vq[q * 4 + 2]) + bq.z);
-                        o.w = (1.f - zv.w) * hv.w + zv.w * tanhf(__uint_as_float(vq[q * 4 + 3]) + bq.w);
-                        *reinterpret_cast<float4*>(p.out + (size_t)row * 64 + c) = o;
-                    }
-                }
-            }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global, one accumulator buffer behind the MMA =====
+        const int quad = warp & 3;   // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int acc = ti & 1;
+            const unsigned acc_phase = (unsigned)(ti >> 1) & 1u;
+            const int row0 = (blockIdx.x + ti * gridDim.x) * kTcM;
+            tmbar_wait(&s_acc_full[acc], acc_phase);
+            if (clk && threadIdx.x == 320 && ti < 4) g_tc_clock[24 + ti] = gtimer();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tc_epilogue(p, tmem + (unsigned)acc * acc_cols, quad, lane, row0, row0 / p.pts_per_sample, s_bias, s_estage, s_part);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            tmbar_arrive(&s_acc_empty[acc]);
+            if (clk && threadIdx.x == 320 && ti < 4) g_tc_clock[28 + ti] = gtimer();
         }
     }
+    __syncwarp();   // the producer / MMA roles run on one lane: re-converge those warps before the CTA-wide barrier
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
     }
+    if (clk && threadIdx.x == 64) g_tc_clock[1] = gtimer();
 }
 
 // hi = tf32(w), lo = tf32(w - hi) of a [rows, ld] weight window [rows, cols] written as [rows_pad, cols_pad] (zero padded)
@@ -422,6 +549,10 @@ static int tc_make_map(CUtensorMap* m, const float* base, long long rows, int co
 
 using namespace pvraft;
 
+extern "C" __attribute__((visibility("default"))) int pvraft_tc_debug_clock(unsigned long long* host64) {
+    return (int)cudaMemcpyFromSymbol(host64, g_tc_clock, sizeof(unsigned long long) * 64);
+}
+
 extern "C" int pvraft_tc_weight_split(const float* w, int rows, int cols, int ld, int col0, int rows_pad, int cols_pad, float* hi,
                                       float* lo, void* stream) {
     if (!w || !hi || !lo || rows <= 0 || cols <= 0 || rows_pad < rows || cols_pad < cols) return fail(PVRAFT_ERR_BAD_ARG, "tc_weight_split: bad argument");
@@ -432,7 +563,7 @@ extern "C" int pvraft_tc_weight_split(const float* w, int rows, int cols, int ld
 
 extern "C" int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream) {
     if (!a || !a->in[0] || !a->w_hi || !a->w_lo || !a->out) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: null pointer");
-    if (a->B <= 0 || a->N <= 0 || a->n_pad < 16 || a->n_pad > 256 || a->n_pad % 16) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: bad shape (n_pad=%d)", a->n_pad);
+    if (a->B <= 0 || a->N <= 0 || a->n_pad < 16 || a->n_pad > 128 || a->n_pad % 16) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: bad shape (n_pad=%d)", a->n_pad);
     if (a->N % kTcM) return fail(PVRAFT_ERR_UNSUPPORTED, "tc_linear: points per sample (%d) must be a multiple of 128", a->N);
     int K = 0;
     for (int s = 0; s < 3; ++s) {
@@ -453,27 +584,32 @@ extern "C" int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream
     p.epi = a->epilogue; p.bias = a->bias; p.bias2 = a->bias2; p.out_act = a->out_act; p.residual = a->residual; p.out = a->out;
     p.out2 = a->out2; p.h = a->h; p.z = a->z; p.out_stats = a->out_stats;
     p.M = (int)M; p.N = a->n_pad; p.K = K; p.cout = a->cout; p.pts_per_sample = a->N;
-    CUtensorMap maps[4], mw_hi, mw_lo;
+    CUtensorMap mw_hi, mw_lo;
     int rc;
     for (int s = 0; s < 3; ++s) {
-        const float* src = a->in[s] ? a->in[s] : a->in[0];
-        const int ch = a->in[s] ? a->in_channels[s] : a->in_channels[0];
+        p.src[s] = a->in[s];
         p.seg_kb[s] = a->in[s] ? a->in_channels[s] / kTcKB : 0;
-        if ((rc = tc_make_map(&maps[s], src, M, ch, ch, kTcM))) return rc;
     }
-    if ((rc = tc_make_map(&maps[3], a->in_min ? a->in_min : a->in[0], M, a->in_channels[0], a->in_channels[0], kTcM))) return rc;
+    p.src_min = a->in_min;
     if ((rc = tc_make_map(&mw_hi, a->w_hi, a->n_pad, K, K, a->n_pad)) || (rc = tc_make_map(&mw_lo, a->w_lo, a->n_pad, K, K, a->n_pad))) return rc;
-    const size_t stage = (size_t)(a->in_min ? 3 : 2) * kTcABytes + (size_t)2 * a->n_pad * kTcKB * 4;
-    const size_t fixed = (size_t)(2 * K + 2 * a->n_pad) * sizeof(float) + 1024 + 64;
-    // ring depth: deep enough to overlap TMA with the MMA, shallow enough that 3 CTAs share an SM (their phases --
-    // load, transform, MMA, epilogue -- then overlap across CTAs); env PVRAFT_TC_STAGES overrides for experiments
-    int stages = (int)(((size_t)kSmemBudget / 3 - fixed) / stage);
+    const size_t a_stage = (size_t)2 * kTcABytes;
+    const size_t w_all = (size_t)(K / kTcKB) * 2 * a->n_pad * kTcKB * 4;          // hi + lo of the whole weight matrix
+    const size_t fixed = (size_t)(2 * K + 2 * a->n_pad + 4 * 32 * 36 + 4 * 32 * 2) * sizeof(float) + 1024 + 64;
+    const size_t budget = (size_t)kSmemBudget - 2048 /* static barriers */ - fixed;
+    // weights stay resident in shared memory whenever they leave room for >= 2 activation stages: re-streaming the
+    // same few KB per tile from every SM hot-spots a handful of L2 slices
+    p.w_resident = w_all + 2 * a_stage <= budget ? 1 : 0;
+    if (const char* e = getenv("PVRAFT_TC_WRES")) p.w_resident = (atoi(e) != 0 && w_all + a_stage <= budget) ? 1 : 0;
+    const size_t stage = a_stage + (p.w_resident ? 0 : (size_t)2 * a->n_pad * kTcKB * 4);
+    int stages = (int)((budget - (p.w_resident ? w_all : 0)) / stage);
     stages = stages < 1 ? 1 : (stages > kTcMaxStages ? kTcMaxStages : stages);
-    if (stages > K / kTcKB) stages = K / kTcKB;
-    if (const char* e = getenv("PVRAFT_TC_STAGES")) { const int v = atoi(e); if (v >= 1 && v <= kTcMaxStages) stages = v; }
+    if (const char* e = getenv("PVRAFT_TC_STAGES")) { const int v = atoi(e); if (v >= 1 && v <= stages) stages = v; }
     p.stages = stages;
-    const size_t smem = stages * stage + fixed;
+    if (const char* e = getenv("PVRAFT_TC_DBG")) p.dbg = atoi(e);
+    const size_t smem = stages * stage + (p.w_resident ? w_all : 0) + fixed;
     if ((rc = opt_in_smem(k_tc_linear, smem))) return rc;
-    k_tc_linear<<<(unsigned)((M + kTcM - 1) / kTcM), kTcThreads, smem, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], mw_hi, mw_lo, p);
+    const long long n_tiles = (M + kTcM - 1) / kTcM;
+    const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
+    k_tc_linear<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(mw_hi, mw_lo, p);
     return check_launch("tc_linear");
 }

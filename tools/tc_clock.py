@@ -1,0 +1,19 @@
+import os, sys, ctypes as C
+os.environ['PVRAFT_TC_DBG'] = '1'
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pvraft_b200 import ops, _lib
+dev = torch.device('cuda:0')
+b, n = 8, 8192
+x = torch.randn(b, n, 64, device=dev); w = torch.randn(64, 64, device=dev)
+tw = ops.tc_weights(w); out = torch.empty(b, n, 64, device=dev)
+lib = C.CDLL(_lib.LIB_PATH)
+for i in range(4):
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(); ops.tc_linear([x], tw, out=out); e.record(); torch.cuda.synchronize()
+    buf = (C.c_ulonglong * 64)()
+    lib.pvraft_tc_debug_clock(buf)
+    t0 = buf[0]
+    rel = lambda a, b: [int(buf[i] - t0) for i in range(a, b)]
+    print('event us %.1f' % (s.elapsed_time(e) * 1e3), 'end', rel(1, 2), 'xform', rel(8, 16), 'mma', rel(16, 24), 'epi_start', rel(24, 28), 'epi_end', rel(28, 32), 'epi_detail', rel(32, 40))
