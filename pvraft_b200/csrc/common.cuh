@@ -85,6 +85,19 @@ __device__ __forceinline__ float apply_act(float x, int act, float slope) {
     return x;
 }
 
+// Branch-free form of apply_act for latency-critical single-warp code paths (a taken branch costs a warp ~25 cycles):
+// y = max(x, lo) + slope * min(x, 0) with (lo, slope) = (-inf, 0) none, (0, 0) ReLU, (0, s) LeakyReLU -- exact in all three.
+struct ActCoef {
+    float lo, slope;
+};
+__device__ __forceinline__ ActCoef act_coef(int act, float slope) {
+    ActCoef c;
+    c.lo = act == PVRAFT_ACT_NONE ? -INFINITY : 0.f;
+    c.slope = act == PVRAFT_ACT_LRELU ? slope : 0.f;
+    return c;
+}
+__device__ __forceinline__ float apply_act(float x, const ActCoef& c) { return fmaf(c.slope, fminf(x, 0.f), fmaxf(x, c.lo)); }
+
 // Contiguous split of `total` items over `parts` workers: worker w gets [begin, end).
 __host__ __device__ __forceinline__ void split_range(long long total, int parts, int w, long long& begin, long long& end) {
     const long long per = (total + parts - 1) / parts;

@@ -89,7 +89,9 @@ k_corr_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const GemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 1024-byte alignment is required by SWIZZLE_128B; the dynamic segment may start lower, so align by hand
-    unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the shared array: an integer round trip would lose the address space
+    // and turn every shared-memory access below into a generic LD/ST
+    unsigned char* tiles = smem_raw + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
     __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages], s_tmem_full;
     __shared__ unsigned s_tmem_base;
     const int warp = warp_id(), lane = lane_id();

@@ -122,6 +122,11 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&v)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ bool telect_one() {
+    unsigned pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ float tsigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
 // epilogue of one accumulator buffer: thread = point (TMEM lane)
@@ -132,24 +137,28 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
     const int gsz = p.cout / PVRAFT_GN_GROUPS;
     const unsigned tl = tacc + ((unsigned)(quad * 32) << 16);
     if (p.epi == TC_EPI_PLAIN) {
+        // Every tile is full (M is a multiple of 128).  This code runs on one warp per scheduler, so it is written for
+        // latency: no per-element branches, addresses hoisted, loads batched ahead of their consumers.
         const bool vec = (p.cout & 3) == 0;
+        const ActCoef oact = act_coef(p.out_act, 0.f);
         float* stg = s_stage + (size_t)quad * 32 * 36;   // this warp's [32 rows][36] staging tile
-        const bool clk = p.dbg && blockIdx.x == 0 && quad == 0 && lane == 0 && row0 == 0;
+        const int rsub = lane >> 3, cq = lane & 7;
+        float* obase = p.out + (size_t)(row0 + quad * 32 + rsub) * p.cout + cq * 4;
+        const size_t ostep = (size_t)4 * p.cout;
+        const bool want_stats = p.out_stats != nullptr;
         for (int c0 = 0; c0 < p.N; c0 += 32) {
             unsigned v[32];
-            if (clk) g_tc_clock[32 + (c0 >> 5) * 4] = gtimer();
             tmem_ld32(tl + (unsigned)c0, v);
-            if (clk) g_tc_clock[33 + (c0 >> 5) * 4] = gtimer();
             float y[32];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0 + q * 4);
-                y[q * 4 + 0] = apply_act(__uint_as_float(v[q * 4 + 0]) + bv.x, p.out_act, 0.f);
-                y[q * 4 + 1] = apply_act(__uint_as_float(v[q * 4 + 1]) + bv.y, p.out_act, 0.f);
-                y[q * 4 + 2] = apply_act(__uint_as_float(v[q * 4 + 2]) + bv.z, p.out_act, 0.f);
-                y[q * 4 + 3] = apply_act(__uint_as_float(v[q * 4 + 3]) + bv.w, p.out_act, 0.f);
+                y[q * 4 + 0] = apply_act(__uint_as_float(v[q * 4 + 0]) + bv.x, oact);
+                y[q * 4 + 1] = apply_act(__uint_as_float(v[q * 4 + 1]) + bv.y, oact);
+                y[q * 4 + 2] = apply_act(__uint_as_float(v[q * 4 + 2]) + bv.z, oact);
+                y[q * 4 + 3] = apply_act(__uint_as_float(v[q * 4 + 3]) + bv.w, oact);
             }
-            if (p.residual != nullptr && live) {   // (rare: FlotRefine.fc) thread-per-row loads, before the statistics
+            if (p.residual != nullptr) {   // (rare: FlotRefine.fc) thread-per-row loads, before the statistics
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
                     if (c0 + i < p.cout) y[i] += __ldg(p.residual + (size_t)row * p.cout + c0 + i);
@@ -162,67 +171,57 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
                 for (int q = 0; q < 8; ++q)
                     *reinterpret_cast<float4*>(stg + lane * 36 + q * 4) = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
                 __syncwarp();
-                if (clk) g_tc_clock[34 + (c0 >> 5) * 4] = gtimer();
-                const int cq = lane & 7, rsub = lane >> 3;
+                float4 t[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = i * 4 + rsub;
-                    const int grow = row0 + quad * 32 + r;
-                    const int c = c0 + cq * 4;
-                    if (grow < p.M && c < p.cout) {
-                        *reinterpret_cast<float4*>(p.out + (size_t)grow * p.cout + c) = *reinterpret_cast<const float4*>(stg + r * 36 + cq * 4);
-                    }
+                for (int i = 0; i < 8; ++i) t[i] = *reinterpret_cast<const float4*>(stg + (i * 4 + rsub) * 36 + cq * 4);
+                if (c0 + cq * 4 < p.cout) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(obase + i * ostep + c0) = t[i];
                 }
-                if (clk) g_tc_clock[35 + (c0 >> 5) * 4] = gtimer();
-            } else if (live) {
+                if (want_stats) {
+                    // lane = column: (sum, sum^2) of this warp's 32 rows, read down the staged tile (conflict-free)
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        const float a = stg[r * 36 + lane];
+                        s1 += a;
+                        s2 = fmaf(a, a, s2);
+                    }
+                    *reinterpret_cast<float2*>(s_part + (size_t)(quad * 128 + c0 + lane) * 2) = make_float2(s1, s2);
+                }
+            } else {
                 float* o = p.out + (size_t)row * p.cout + c0;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     if (c0 + i < p.cout) o[i] = y[i];
                 }
             }
-            if (p.out_stats != nullptr) {
-                // 8 partial (sum, sum^2) pairs per thread: sub-group j covers columns [4j, 4j+4) of this step; every
-                // GroupNorm group is a union of whole sub-groups (group size is a multiple of 4)
-                float s1[8], s2[8];
+        }
+        if (want_stats) {
+            // combine the 4 epilogue warps and the columns of each GroupNorm group: thread t owns column t
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            const int t = quad * 32 + lane;
+            double a1 = 0.0, a2 = 0.0;
+            if (t < p.N) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    s1[j] = 0.f; s2[j] = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float a = live ? y[j * 4 + i] : 0.f;
-                        s1[j] += a;
-                        s2[j] = fmaf(a, a, s2[j]);
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        s1[j] += __shfl_xor_sync(kFull, s1[j], o);
-                        s2[j] += __shfl_xor_sync(kFull, s2[j], o);
-                    }
-                }
-                if (lane < 8) {   // lane j parks sub-group j of this warp; the 4 warps are combined below
-                    float a1 = 0.f, a2 = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { a1 = lane == j ? s1[j] : a1; a2 = lane == j ? s2[j] : a2; }
-                    s_part[(quad * 32 + (c0 >> 2) + lane) * 2 + 0] = a1;
-                    s_part[(quad * 32 + (c0 >> 2) + lane) * 2 + 1] = a2;
+                for (int w = 0; w < 4; ++w) {
+                    const float2 pr = *reinterpret_cast<const float2*>(s_part + (size_t)(w * 128 + t) * 2);
+                    a1 += (double)pr.x;
+                    a2 += (double)pr.y;
                 }
             }
-        }
-        if (p.out_stats != nullptr) {
-            // combine the 4 epilogue warps: one double atomic per (sub-group, moment) and tile instead of four
-            asm volatile("bar.sync 2, 128;" ::: "memory");
-            const int t = quad * 32 + lane;   // 0..127
-            const int nsub = p.N >> 2;        // sub-groups of 4 columns
-            if (t < nsub * 2) {
-                const int sg = t >> 1, m = t & 1;
-                const double tot = (double)s_part[(0 * 32 + sg) * 2 + m] + (double)s_part[(1 * 32 + sg) * 2 + m] +
-                                   (double)s_part[(2 * 32 + sg) * 2 + m] + (double)s_part[(3 * 32 + sg) * 2 + m];
-                const int c = sg * 4;
-                if (c < p.cout) atomicAdd(p.out_stats + (size_t)sample * 16 + (c / gsz) * 2 + m, tot);
+            if ((gsz & (gsz - 1)) == 0 && gsz <= 32) {   // groups are aligned runs of gsz lanes
+                for (int o = gsz >> 1; o > 0; o >>= 1) {
+                    a1 += __shfl_xor_sync(kFull, a1, o);
+                    a2 += __shfl_xor_sync(kFull, a2, o);
+                }
+                if ((t & (gsz - 1)) == 0 && t < p.cout) {
+                    atomicAdd(p.out_stats + (size_t)sample * 16 + (t / gsz) * 2 + 0, a1);
+                    atomicAdd(p.out_stats + (size_t)sample * 16 + (t / gsz) * 2 + 1, a2);
+                }
+            } else if (t < p.cout) {
+                atomicAdd(p.out_stats + (size_t)sample * 16 + (t / gsz) * 2 + 0, a1);
+                atomicAdd(p.out_stats + (size_t)sample * 16 + (t / gsz) * 2 + 1, a2);
             }
             asm volatile("bar.sync 2, 128;" ::: "memory");
         }
@@ -284,14 +283,24 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
 // A CTA walks tiles blockIdx.x, +gridDim.x, ...; the operand ring and the two accumulators run across tile boundaries.
 constexpr int kTcXform = 256;   // transform threads
 
-struct XformRegs {
-    float4 a[4], m[4];
+// Position of one pipeline role in the (tile, k-block) walk and in the operand ring; advanced without divisions (a
+// runtime integer division is a ~100-cycle dependent chain, paid per step by warps that have nothing to hide it behind)
+struct TcCursor {
+    int ti = 0, kb = 0, s = 0;
+    unsigned phase = 0;
+    __device__ __forceinline__ void next(int num_kb, int S) {
+        if (++kb == num_kb) { kb = 0; ++ti; }
+        if (++s == S) { s = 0; phase ^= 1u; }
+    }
 };
+constexpr int kTcDepth = 4;     // k-blocks of activations in flight per loader thread (cp.async groups)
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the shared array: an integer round trip would lose the address space
+    // and turn every shared-memory access below into a generic LD/ST
+    unsigned char* tiles = smem_raw + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
     // stage layout: [A hi 16K][A lo 16K][W hi N*128][W lo N*128, only when the weights are streamed];
     // resident weights live behind the ring as num_kb x [W hi][W lo]
     const int w_bytes = p.N * kTcKB * 4;
@@ -304,7 +313,7 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
     float* s_shift = s_scale + p.K;
     float* s_bias = s_shift + p.K;                                                // [2 * N]
     float* s_estage = s_bias + 2 * p.N;                                           // [4 warps][32][36] epilogue staging
-    float* s_part = s_estage + 4 * 32 * 36;                                       // [4 warps][32 sub-groups][2]
+    float* s_part = s_estage + 4 * 32 * 36;                                       // [4 warps][128 columns][2]
     __shared__ __align__(8) unsigned long long s_full[kTcMaxStages], s_ready[kTcMaxStages], s_empty[kTcMaxStages];
     __shared__ __align__(8) unsigned long long s_acc_full[2], s_acc_empty[2], s_w_full;
     __shared__ unsigned s_tmem_base;
@@ -322,8 +331,8 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_lo) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < S; ++s) { tmbar_init(&s_full[s], 1); tmbar_init(&s_ready[s], kTcXform); tmbar_init(&s_empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { tmbar_init(&s_acc_full[a], 1); tmbar_init(&s_acc_empty[a], 128); }
+        for (int s = 0; s < S; ++s) { tmbar_init(&s_full[s], 1); tmbar_init(&s_ready[s], kTcXform / 32); tmbar_init(&s_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { tmbar_init(&s_acc_full[a], 1); tmbar_init(&s_acc_empty[a], 4); }
         tmbar_init(&s_w_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -341,6 +350,18 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem = s_tmem_base;
+    if (p.dbg & 2) {   // isolated epilogue timing: nothing else runs on the SM
+        if (warp >= 10) {
+            for (int rep = 0; rep < 3; ++rep) {
+                if (clk && threadIdx.x == 320) g_tc_clock[44 + rep] = clock64();
+                if (clk && threadIdx.x == 320) g_tc_clock[40 + rep] = gtimer();
+                tc_epilogue(p, tmem, warp & 3, lane, blockIdx.x * kTcM, 0, s_bias, s_estage, s_part);
+            }
+            if (clk && threadIdx.x == 320) g_tc_clock[43] = gtimer();
+            if (clk && threadIdx.x == 320) g_tc_clock[47] = clock64();
+        }
+        __syncthreads();
+    }
 
     if (warp == 0) {
         // ===== weight producer =====
@@ -352,10 +373,10 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
                     ttma_load_2d(w_res + (size_t)kb * 2 * w_bytes + w_bytes, &map_w_lo, &s_w_full, kb * kTcKB, 0);
                 }
             } else {
-                for (int step = 0; step < total_steps; ++step) {
-                    const int s = step % S, kb = step % num_kb;
-                    const unsigned phase = (unsigned)(step / S) & 1u;
-                    tmbar_wait(&s_empty[s], phase ^ 1u);
+                TcCursor cw;
+                for (int step = 0; step < total_steps; ++step, cw.next(num_kb, S)) {
+                    const int s = cw.s, kb = cw.kb;
+                    tmbar_wait(&s_empty[s], cw.phase ^ 1u);
                     unsigned char* st = tiles + (size_t)s * stage_bytes;
                     tmbar_expect_tx(&s_full[s], (unsigned)(2 * w_bytes));
                     ttma_load_2d(st + w_off, &map_w_hi, &s_full[s], kb * kTcKB, 0);
@@ -365,19 +386,22 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        // The whole warp walks the loop (convergent control flow keeps the descriptor arithmetic on the uniform datapath)
+        // and one elected lane issues; under `if (lane == 0)` the compiler wraps every UTCHMMA in an election loop.
+        {
             const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(p.N >> 3) << 17) | ((unsigned)(kTcM >> 4) << 24);
             if (p.w_resident) tmbar_wait(&s_w_full, 0u);
             int step = 0;
+            TcCursor cm;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int acc = ti & 1;
                 const unsigned acc_phase = (unsigned)(ti >> 1) & 1u;
                 tmbar_wait(&s_acc_empty[acc], acc_phase ^ 1u);   // the epilogue has drained this accumulator buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const unsigned tacc = tmem + (unsigned)acc * acc_cols;
-                for (int kb = 0; kb < num_kb; ++kb, ++step) {
-                    const int s = step % S;
-                    const unsigned phase = (unsigned)(step / S) & 1u;
+                for (int kb = 0; kb < num_kb; ++kb, ++step, cm.next(num_kb, S)) {
+                    const int s = cm.s;
+                    const unsigned phase = cm.phase;
                     tmbar_wait(&s_ready[s], phase);               // transformed activations are in place
                     if (!p.w_resident) tmbar_wait(&s_full[s], phase);   // streamed weight boxes have landed
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -385,50 +409,64 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
                     const unsigned long long a_hi = tumma_desc(st), a_lo = tumma_desc(st + kTcABytes);
                     const unsigned char* wb = p.w_resident ? w_res + (size_t)kb * 2 * w_bytes : st + w_off;
                     const unsigned long long b_hi = tumma_desc(wb), b_lo = tumma_desc(wb + w_bytes);
+                    if (telect_one()) {
 #pragma unroll
-                    for (int k = 0; k < kTcKB / 8; ++k) {
-                        const unsigned long long off = (unsigned long long)(k * 2);
-                        tumma_tf32(tacc, a_hi + off, b_hi + off, idesc, (kb | k) != 0 ? 1u : 0u);
-                        tumma_tf32(tacc, a_lo + off, b_hi + off, idesc, 1u);
-                        tumma_tf32(tacc, a_hi + off, b_lo + off, idesc, 1u);
+                        for (int k = 0; k < kTcKB / 8; ++k) {
+                            const unsigned long long off = (unsigned long long)(k * 2);
+                            tumma_tf32(tacc, a_hi + off, b_hi + off, idesc, (kb | k) != 0 ? 1u : 0u);
+                            tumma_tf32(tacc, a_lo + off, b_hi + off, idesc, 1u);
+                            tumma_tf32(tacc, a_hi + off, b_lo + off, idesc, 1u);
+                        }
+                        tumma_commit(&s_empty[s]);
+                        if (kb == num_kb - 1) tumma_commit(&s_acc_full[acc]);
+                        if (clk && step < 8) g_tc_clock[16 + step] = gtimer();
                     }
-                    tumma_commit(&s_empty[s]);
-                    if (clk && step < 8) g_tc_clock[16 + step] = gtimer();
+                    __syncwarp();
                 }
-                tumma_commit(&s_acc_full[acc]);
             }
         }
     } else if (warp < 10) {
         // ===== activation loaders + transform =====
         const int t = threadIdx.x - 64;   // 0..255: chunk c = t + 256*i, i < 4, of the 1024 16-byte chunks of a k-block
-        int cur_sample = -1;
-        auto issue = [&](XformRegs& R, int step) {
-            const int ti = step / num_kb, kb = step - ti * num_kb;
-            const int row0 = (blockIdx.x + ti * gridDim.x) * kTcM;
-            int seg = 0, kk = kb;   // which source tensor does this k-block come from?
-            if (kk >= p.seg_kb[0]) { kk -= p.seg_kb[0]; seg = 1; if (kk >= p.seg_kb[1]) { kk -= p.seg_kb[1]; seg = 2; } }
-            const float* src = p.src[seg];
-            const int ld = p.seg_kb[seg] * kTcKB;
+        const ActCoef iact = act_coef(p.in_act, p.in_slope);
+        // cp.async ring: thread t moves the same four 16-byte chunks of every k-block that it later transforms, so the
+        // only wait it needs is on its own copy groups; D k-blocks are in flight per thread (D = min(4, stages - 1))
+        const int D = min(kTcDepth, S - 1);
+        TcCursor ci, cp;   // issue / process positions
+        const int tiles_per_sample = p.pts_per_sample / kTcM;
+        int next_sample_tile = 0;   // first tile index (global) of the sample after cur_sample
+        auto issue = [&](int step) {
+            if (step < total_steps) {
+                const int ti = ci.ti, kb = ci.kb;
+                const int row0 = (blockIdx.x + ti * gridDim.x) * kTcM;
+                int seg = 0, kk = kb;   // which source tensor does this k-block come from?
+                if (kk >= p.seg_kb[0]) { kk -= p.seg_kb[0]; seg = 1; if (kk >= p.seg_kb[1]) { kk -= p.seg_kb[1]; seg = 2; } }
+                const float* src = p.src[seg];
+                const int ld = p.seg_kb[seg] * kTcKB;
+                const int s = ci.s;
+                tmbar_wait(&s_empty[s], ci.phase ^ 1u);   // the MMAs that read this stage last time have retired
+                const unsigned st = tsu32(tiles + (size_t)s * stage_bytes);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c = t + i * kTcXform, r = c >> 3, lc = c & 7;
-                const long long grow = (long long)row0 + r;
-                R.a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                R.m[i] = R.a[i];
-                if (grow < p.M) {
-                    const size_t off = (size_t)grow * ld + kk * kTcKB + lc * 4;
-                    R.a[i] = __ldg(reinterpret_cast<const float4*>(src + off));
-                    if (p.minmax) R.m[i] = __ldg(reinterpret_cast<const float4*>(p.src_min + off));
+                for (int i = 0; i < 4; ++i) {
+                    const int c = t + i * kTcXform, r = c >> 3, lc = c & 7;
+                    const size_t off = (size_t)(row0 + r) * ld + kk * kTcKB + lc * 4;
+                    // K-major SWIZZLE_128B: 16-byte chunk lc of row r lives at chunk (lc ^ (r & 7)) of the row's 128 bytes
+                    const unsigned dst = st + (unsigned)(r * 128 + ((lc ^ (r & 7)) << 4));
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + off) : "memory");
+                    if (p.minmax) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)kTcABytes), "l"(p.src_min + off) : "memory");
                 }
+                ci.next(num_kb, S);
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");   // (an empty group past the end keeps the count uniform)
         };
-        auto process = [&](const XformRegs& R, int step) {
-            const int ti = step / num_kb, kb = step - ti * num_kb;
-            const int s = step % S;
-            const unsigned phase = (unsigned)(step / S) & 1u;
+        auto process = [&](int step) {
+            const int ti = cp.ti, kb = cp.kb;
+            const int s = cp.s;
             if (p.in_stats != nullptr && kb == 0) {
-                const int sample = ((blockIdx.x + ti * gridDim.x) * kTcM) / p.pts_per_sample;
-                if (sample != cur_sample) {   // folded GroupNorm affine of every input channel of this sample
+                const int tile = blockIdx.x + ti * gridDim.x;
+                if (tile >= next_sample_tile) {   // folded GroupNorm affine of every input channel of this sample
+                    const int sample = tile / tiles_per_sample;
+                    next_sample_tile = (sample + 1) * tiles_per_sample;
                     asm volatile("bar.sync 1, 256;" ::: "memory");   // everyone is done with the previous sample's table
                     const int gsz = p.K / PVRAFT_GN_GROUPS;
                     for (int k = t; k < p.K; k += kTcXform) {
@@ -437,48 +475,52 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
                         s_shift[k] = af.shift;
                     }
                     asm volatile("bar.sync 1, 256;" ::: "memory");
-                    cur_sample = sample;
                 }
             }
-            tmbar_wait(&s_empty[s], phase ^ 1u);   // the MMAs that read this stage last time have retired
+            switch (D - 1) {   // all but the D-1 youngest copy groups of this thread have landed
+                case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+                case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+                case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+                default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+            }
             unsigned char* st = tiles + (size_t)s * stage_bytes;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int c = t + i * kTcXform, r = c >> 3, lc = c & 7;
-                float4 x = R.a[i];
+                const int off = r * 128 + ((lc ^ (r & 7)) << 4);
+                float4 x = *reinterpret_cast<const float4*>(st + off);
                 if (p.in_stats != nullptr) {
                     const int k = kb * kTcKB + lc * 4;
                     const float4 sc = *reinterpret_cast<const float4*>(s_scale + k);
                     const float4 sh = *reinterpret_cast<const float4*>(s_shift + k);
                     if (p.minmax) {
-                        x.x = sc.x < 0.f ? R.m[i].x : x.x; x.y = sc.y < 0.f ? R.m[i].y : x.y;
-                        x.z = sc.z < 0.f ? R.m[i].z : x.z; x.w = sc.w < 0.f ? R.m[i].w : x.w;
+                        const float4 mn = *reinterpret_cast<const float4*>(st + kTcABytes + off);
+                        x.x = sc.x < 0.f ? mn.x : x.x; x.y = sc.y < 0.f ? mn.y : x.y;
+                        x.z = sc.z < 0.f ? mn.z : x.z; x.w = sc.w < 0.f ? mn.w : x.w;
                     }
-                    x.x = apply_act(fmaf(x.x, sc.x, sh.x), p.in_act, p.in_slope);
-                    x.y = apply_act(fmaf(x.y, sc.y, sh.y), p.in_act, p.in_slope);
-                    x.z = apply_act(fmaf(x.z, sc.z, sh.z), p.in_act, p.in_slope);
-                    x.w = apply_act(fmaf(x.w, sc.w, sh.w), p.in_act, p.in_slope);
+                    x.x = apply_act(fmaf(x.x, sc.x, sh.x), iact);
+                    x.y = apply_act(fmaf(x.y, sc.y, sh.y), iact);
+                    x.z = apply_act(fmaf(x.z, sc.z, sh.z), iact);
+                    x.w = apply_act(fmaf(x.w, sc.w, sh.w), iact);
                 }
                 float4 hi, lo;
                 hi.x = tf32_rna(x.x); hi.y = tf32_rna(x.y); hi.z = tf32_rna(x.z); hi.w = tf32_rna(x.w);
                 lo.x = tf32_rna(x.x - hi.x); lo.y = tf32_rna(x.y - hi.y); lo.z = tf32_rna(x.z - hi.z); lo.w = tf32_rna(x.w - hi.w);
-                // K-major SWIZZLE_128B: 16-byte chunk lc of row r lives at chunk (lc ^ (r & 7)) of the row's 128 bytes
-                const int off = r * 128 + ((lc ^ (r & 7)) << 4);
-                *reinterpret_cast<float4*>(st + off) = hi;
+                *reinterpret_cast<float4*>(st + off) = hi;   // in place: raw -> hi; the lo half of the stage held the min array
                 *reinterpret_cast<float4*>(st + kTcABytes + off) = lo;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
-            tmbar_arrive(&s_ready[s]);
+            __syncwarp();
+            if (lane == 0) tmbar_arrive(&s_ready[s]);   // one arrival per loader warp
             if (clk && t == 0 && step < 8) g_tc_clock[8 + step] = gtimer();
+            cp.next(num_kb, S);
         };
-        XformRegs RA, RB;
-        if (total_steps > 0) issue(RA, 0);
-        for (int step = 0; step < total_steps; step += 2) {
-            if (step + 1 < total_steps) issue(RB, step + 1);
-            process(RA, step);
-            if (step + 2 < total_steps) issue(RA, step + 2);
-            if (step + 1 < total_steps) process(RB, step + 1);
+        for (int d = 0; d < D; ++d) issue(d);
+        for (int step = 0; step < total_steps; ++step) {
+            process(step);
+            issue(step + D);
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else {
         // ===== epilogue: TMEM -> registers -> global, one accumulator buffer behind the MMA =====
         const int quad = warp & 3;   // a warp may only touch TMEM lanes 32*(warp%4) .. +31
@@ -491,7 +533,8 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             tc_epilogue(p, tmem + (unsigned)acc * acc_cols, quad, lane, row0, row0 / p.pts_per_sample, s_bias, s_estage, s_part);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            tmbar_arrive(&s_acc_empty[acc]);
+            __syncwarp();
+            if (lane == 0) tmbar_arrive(&s_acc_empty[acc]);   // one arrival per epilogue warp
             if (clk && threadIdx.x == 320 && ti < 4) g_tc_clock[28 + ti] = gtimer();
         }
     }
@@ -594,7 +637,7 @@ extern "C" int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream
     if ((rc = tc_make_map(&mw_hi, a->w_hi, a->n_pad, K, K, a->n_pad)) || (rc = tc_make_map(&mw_lo, a->w_lo, a->n_pad, K, K, a->n_pad))) return rc;
     const size_t a_stage = (size_t)2 * kTcABytes;
     const size_t w_all = (size_t)(K / kTcKB) * 2 * a->n_pad * kTcKB * 4;          // hi + lo of the whole weight matrix
-    const size_t fixed = (size_t)(2 * K + 2 * a->n_pad + 4 * 32 * 36 + 4 * 32 * 2) * sizeof(float) + 1024 + 64;
+    const size_t fixed = (size_t)(2 * K + 2 * a->n_pad + 4 * 32 * 36 + 4 * 128 * 2) * sizeof(float) + 1024 + 64;
     const size_t budget = (size_t)kSmemBudget - 2048 /* static barriers */ - fixed;
     // weights stay resident in shared memory whenever they leave room for >= 2 activation stages: re-streaming the
     // same few KB per tile from every SM hot-spots a handful of L2 slices

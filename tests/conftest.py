@@ -55,3 +55,27 @@ def rel_err(a, b):
     a = a.double()
     b = b.double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+@pytest.fixture(autouse=True)
+def _poison_uninitialised(monkeypatch):
+    """PVRAFT_POISON=1: every torch.empty/empty_like/new_empty allocation is filled with NaN (floats) or a huge
+    value (ints), so that any kernel reading memory it was supposed to have been given initialised shows up as a
+    hard failure instead of a once-in-a-while mismatch."""
+    if os.environ.get('PVRAFT_POISON') != '1':
+        yield
+        return
+    real_empty, real_like = torch.empty, torch.empty_like
+
+    def fill(t):
+        if t.is_floating_point():
+            t.fill_(float('nan'))
+        elif t.dtype != torch.bool:
+            t.fill_(torch.iinfo(t.dtype).max // 2)
+        return t
+
+    monkeypatch.setattr(torch, 'empty', lambda *a, **k: fill(real_empty(*a, **k)))
+    monkeypatch.setattr(torch, 'empty_like', lambda *a, **k: fill(real_like(*a, **k)))
+    real_new = torch.Tensor.new_empty
+    monkeypatch.setattr(torch.Tensor, 'new_empty', lambda self, *a, **k: fill(real_new(self, *a, **k)))
+    yield

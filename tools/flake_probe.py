@@ -9,7 +9,7 @@ g=T.golden_graph(arr,dev)
 inp=torch.relu(arr['fct1'][:,64:]).to(dev)
 worst={}
 for rep in range(60):
-    net=torch.tanh(arr['fct1'][:,:64]).to(dev)
+    net=torch.tanh(arr['fct1'][:,:64].double()).float().to(dev)
     # churn the allocator a bit
     junk=[torch.randn(1000+rep*37,device=dev) for _ in range(rep%5)]
     with torch.no_grad():
