@@ -167,7 +167,7 @@ typedef struct pvraft_tc_linear_args {
     const float* in[3];     /* activation sources [B,N,in_channels[i]]; unused entries NULL */
     int in_channels[3];
     const float* in_min;    /* per-channel minima paired with in[0] (GroupNorm prologue with max/min selection) or NULL */
-    const double* in_stats; /* [B,8,2] -> GroupNorm prologue on the (single) source, or NULL */
+    const double* in_stats; /* [B,8,2] -> GroupNorm prologue on source 0 (further sources are taken as they are), or NULL */
     const float* in_gamma;
     const float* in_beta;
     double in_count;
@@ -187,6 +187,8 @@ typedef struct pvraft_tc_linear_args {
     double* out_stats;      /* [B,8,2] accumulated, or NULL */
     int epilogue;           /* pvraft_tc_epilogue */
     int B, N;
+    const float* tail;      /* PLAIN, or NULL: [B,N,3] copied into output columns cout..cout+2 (out row stride cout+3 = n_pad):
+                               the MotionEncoder's `cat([out, flow])`, model/update.py:20 */
 } pvraft_tc_linear_args;
 
 PVRAFT_API int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream);
@@ -238,6 +240,32 @@ typedef struct pvraft_corrfeat_args {
 } pvraft_corrfeat_args;
 
 PVRAFT_API int pvraft_corr_feature_fwd(const pvraft_corrfeat_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * The ALU part of the feature head, for the tcgen05 path (the 1x1 convolutions around it run as pvraft_tc_linear_fwd):
+ *   kfeat[b,n,c] = max over the 32 selected candidates of PReLU(GroupNorm(knn_conv.0(f)))      (model/corr.py:86-92)
+ *   cflow[b,n,c] = relu(conv_flow(flow))                                                        (model/update.py:17)
+ * knn_sel [B,N,32,4] and moments [B,PVRAFT_MOMENTS] come from pvraft_corr_lookup_fwd; the GroupNorm statistics follow
+ * from the moments, so no pass over the [B,64,N,32] tensor of the reference is needed.  flow/cflow may be NULL.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct pvraft_knn_branch_args {
+    const float* knn_sel;
+    const double* moments;
+    const float* w_knn;     /* corr_block.knn_conv.0.weight [64,4] */
+    const float* b_knn;     /* corr_block.knn_conv.0.bias   [64]   */
+    const float* gnk_gamma; /* corr_block.knn_conv.1.weight [64]   */
+    const float* gnk_beta;  /* corr_block.knn_conv.1.bias   [64]   */
+    const float* preluk;    /* corr_block.knn_conv.2.weight [1]    */
+    float preluk_host;      /* the same slope as known to the host (selects the convex fast path without a device read);
+                               NaN = read it from `preluk` (costs one stream synchronisation) */
+    float* kfeat;           /* [B,N,64] */
+    const float* flow;      /* [B,N,3] or NULL */
+    const float* w_cf; const float* b_cf;   /* update_block.motion_encoder.conv_flow [64,3],[64] */
+    float* cflow;           /* [B,N,64] or NULL */
+    int B, N;
+} pvraft_knn_branch_args;
+
+PVRAFT_API int pvraft_knn_branch_fwd(const pvraft_knn_branch_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * ConvGRU.  Replaces model/update.py:31-40 with x = [inp, motion] (update.py:84).

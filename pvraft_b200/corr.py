@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .ops import ACT_NONE
+from .ops import ACT_LRELU, ACT_NONE, ACT_RELU
 
 
 def _w(p):
@@ -145,6 +145,39 @@ class CorrBlock(nn.Module):
             motion_args(a, keep)
         ops.corr_feature(a)
         return corr, keep
+
+    def feature_motion_tc(self, coords, flow, motion_encoder):
+        """Lookup + feature head + MotionEncoder with every 1x1 convolution on the tcgen05 tensor cores
+        (model/corr.py:42-45 and model/update.py:15-21): coords, flow [B,N,3] -> (corr [B,N,64], motion [B,N,64]).
+        Needs ops.tc_supported(N)."""
+        b, n, _ = coords.shape
+        dev = coords.device
+        nvox = self.num_levels * 27
+        kpad = (nvox + 31) // 32 * 32
+        oc, kc, me = self.out_conv, self.knn_conv, motion_encoder
+        stats = ops.new_stats(b, dev, 1)
+        lk = self.lookup(coords, vox_ld=kpad)
+        y1 = ops.tc_linear([lk['vox']], ops.tc_weights(oc[0].weight, cols=nvox, k_pad=kpad), _w(oc[0].bias), out_stats=stats[0])
+        # kNN branch (ALU) + flow embedding
+        a = _lib.KnnBranchArgs()
+        a.knn_sel, a.moments = ops._p(lk['knn_sel']), ops._p(lk['moments'], torch.float64)
+        a.w_knn, a.b_knn = ops._p(_w(kc[0].weight)), ops._p(_w(kc[0].bias))
+        a.gnk_gamma, a.gnk_beta, a.preluk = ops._p(_w(kc[1].weight)), ops._p(_w(kc[1].bias)), ops._p(_w(kc[2].weight))
+        a.preluk_host = ops.derived((kc[2].weight,), 'slope', lambda w: float(w.detach().reshape(-1)[0]))
+        kfeat = torch.empty(b, n, 64, dtype=torch.float32, device=dev)
+        cflow = torch.empty(b, n, 64, dtype=torch.float32, device=dev)
+        a.kfeat, a.flow, a.cflow = ops._p(kfeat), ops._p(flow), ops._p(cflow)
+        a.w_cf, a.b_cf = ops._p(_w(me.conv_flow.weight)), ops._p(_w(me.conv_flow.bias))
+        a.B, a.N = b, n
+        ops.knn_branch(a)
+        # corr = out_conv[3](PReLU(GN(y1))) + knn_out(kfeat): one GEMM over K = 128 + 64
+        bias = ops.derived((oc[3].bias, self.knn_out.bias), 'sum', lambda x, y: (x.detach() + y.detach()).contiguous())
+        corr = ops.tc_linear([y1, kfeat], ops.tc_weights((oc[3].weight, self.knn_out.weight), kcat=True), bias,
+                             in_stats=stats[0], in_gamma=_w(oc[1].weight), in_beta=_w(oc[1].bias), in_count=float(n) * 16.0,
+                             in_act=ACT_LRELU, in_slope=ops.derived((oc[2].weight,), 'slope', lambda w: float(w.detach().reshape(-1)[0])))
+        cc = ops.tc_linear([corr], ops.tc_weights(me.conv_corr.weight), _w(me.conv_corr.bias), out_act=ACT_RELU)
+        motion = ops.tc_linear([cc, cflow], ops.tc_weights(me.conv.weight), _w(me.conv.bias), out_act=ACT_RELU, tail=flow)
+        return corr, motion
 
     def __call__(self, coords):
         """model/corr.py:44-45 -> [B,64,N]."""

@@ -68,6 +68,7 @@ extern "C" int pvraft_sizeof(int which) {
         case 2: return (int)sizeof(pvraft_gru_args);
         case 3: return (int)sizeof(pvraft_flowout_args);
         case 4: return (int)sizeof(pvraft_tc_linear_args);
+        case 5: return (int)sizeof(pvraft_knn_branch_args);
         default: return -1;
     }
 }

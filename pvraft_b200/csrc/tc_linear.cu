@@ -21,7 +21,7 @@
 
 namespace pvraft {
 
-constexpr int kTcThreads = 448;   // weight TMA | MMA | 8 load+transform warps | 4 epilogue warps
+constexpr int kTcThreads = 576;   // TMA producer | MMA | 8 transform warps (two groups) | 8 epilogue warps
 constexpr int kTcM = 128, kTcKB = 32;
 constexpr int kTcABytes = kTcM * kTcKB * 4;   // 16 KB: one activation box
 constexpr int kTcMaxStages = 6;
@@ -58,6 +58,9 @@ struct TcParams {
     int stages;               // depth of the shared-memory ring (1..4)
     int w_resident;           // 1: all weight boxes are loaded once per CTA and stay in shared memory
     int dbg;                  // 1: CTA 0 records a globaltimer timeline into g_tc_clock
+    int gn_kb;                // k-blocks (from the start: source 0) that go through the GroupNorm prologue
+    int out_ld;               // row stride of `out` in floats (cout, or cout + 3 with a tail)
+    const float* tail;        // [M,3] copied into output columns cout..cout+2, or nullptr
 };
 
 __device__ __forceinline__ unsigned tsu32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -130,7 +133,7 @@ __device__ __forceinline__ bool telect_one() {
 __device__ __forceinline__ float tsigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
 // epilogue of one accumulator buffer: thread = point (TMEM lane)
-__device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, int quad, int lane, int row0, int sample,
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, int quad, int half, int lane, int row0, int sample,
                                             const float* __restrict__ s_bias, float* __restrict__ s_stage, float* __restrict__ s_part) {
     const int row = row0 + quad * 32 + lane;
     const bool live = row < p.M;
@@ -139,14 +142,14 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
     if (p.epi == TC_EPI_PLAIN) {
         // Every tile is full (M is a multiple of 128).  This code runs on one warp per scheduler, so it is written for
         // latency: no per-element branches, addresses hoisted, loads batched ahead of their consumers.
-        const bool vec = (p.cout & 3) == 0;
+        const bool vec = (p.out_ld & 3) == 0;
         const ActCoef oact = act_coef(p.out_act, 0.f);
-        float* stg = s_stage + (size_t)quad * 32 * 36;   // this warp's [32 rows][36] staging tile
+        float* stg = s_stage + (size_t)(half * 4 + quad) * 32 * 36;   // this warp's [32 rows][36] staging tile
         const int rsub = lane >> 3, cq = lane & 7;
-        float* obase = p.out + (size_t)(row0 + quad * 32 + rsub) * p.cout + cq * 4;
-        const size_t ostep = (size_t)4 * p.cout;
+        float* obase = p.out + (size_t)(row0 + quad * 32 + rsub) * p.out_ld + cq * 4;
+        const size_t ostep = (size_t)4 * p.out_ld;
         const bool want_stats = p.out_stats != nullptr;
-        for (int c0 = 0; c0 < p.N; c0 += 32) {
+        for (int c0 = half * 32; c0 < p.N; c0 += 64) {
             unsigned v[32];
             tmem_ld32(tl + (unsigned)c0, v);
             float y[32];
@@ -163,6 +166,10 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
                 for (int i = 0; i < 32; ++i)
                     if (c0 + i < p.cout) y[i] += __ldg(p.residual + (size_t)row * p.cout + c0 + i);
             }
+            if (p.tail != nullptr && c0 + 32 == p.out_ld) {   // last three columns of the row carry the tail (cat([out, flow]))
+                const float* tp = p.tail + (size_t)row * 3;
+                y[29] = __ldg(tp); y[30] = __ldg(tp + 1); y[31] = __ldg(tp + 2);
+            }
             if (vec) {
                 // transpose through shared memory so that a store instruction writes 4 rows x 128 contiguous bytes
                 // (thread-per-row stores would scatter 32 half-filled sectors per instruction)
@@ -174,7 +181,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
                 float4 t[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) t[i] = *reinterpret_cast<const float4*>(stg + (i * 4 + rsub) * 36 + cq * 4);
-                if (c0 + cq * 4 < p.cout) {
+                if (c0 + cq * 4 < p.out_ld) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(obase + i * ostep + c0) = t[i];
                 }
@@ -190,17 +197,17 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
                     *reinterpret_cast<float2*>(s_part + (size_t)(quad * 128 + c0 + lane) * 2) = make_float2(s1, s2);
                 }
             } else {
-                float* o = p.out + (size_t)row * p.cout + c0;
+                float* o = p.out + (size_t)row * p.out_ld + c0;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    if (c0 + i < p.cout) o[i] = y[i];
+                    if (c0 + i < p.out_ld) o[i] = y[i];
                 }
             }
         }
         if (want_stats) {
             // combine the 4 epilogue warps and the columns of each GroupNorm group: thread t owns column t
-            asm volatile("bar.sync 2, 128;" ::: "memory");
-            const int t = quad * 32 + lane;
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            const int t = (half * 4 + quad) * 32 + lane;   // 0..255; threads 0..N-1 own one column each
             double a1 = 0.0, a2 = 0.0;
             if (t < p.N) {
 #pragma unroll
@@ -223,11 +230,11 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
                 atomicAdd(p.out_stats + (size_t)sample * 16 + (t / gsz) * 2 + 0, a1);
                 atomicAdd(p.out_stats + (size_t)sample * 16 + (t / gsz) * 2 + 1, a2);
             }
-            asm volatile("bar.sync 2, 128;" ::: "memory");
+            asm volatile("bar.sync 3, 256;" ::: "memory");
         }
     } else if (p.epi == TC_EPI_GRU_ZR) {
         // accumulator columns 0..63 = z pre-activation, 64..127 = r pre-activation (model/update.py:34-35)
-        for (int c0 = 0; c0 < 64; c0 += 32) {
+        for (int c0 = half * 32; c0 < 64; c0 += 64) {
             unsigned vz[32], vr[32];
             tmem_ld32(tl + (unsigned)c0, vz);
             tmem_ld32(tl + (unsigned)(64 + c0), vr);
@@ -250,7 +257,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
         }
     } else {
         // q = tanh(acc + b); h' = (1 - z) h + z q   (model/update.py:37-39)
-        for (int c0 = 0; c0 < 64; c0 += 32) {
+        for (int c0 = half * 32; c0 < 64; c0 += 64) {
             unsigned vq[32];
             tmem_ld32(tl + (unsigned)c0, vq);
             if (live) {
@@ -293,10 +300,11 @@ struct TcCursor {
         if (++s == S) { s = 0; phase ^= 1u; }
     }
 };
-constexpr int kTcDepth = 4;     // k-blocks of activations in flight per loader thread (cp.async groups)
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams p) {
+k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+            const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+            const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_min, const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 1024-byte alignment by pointer arithmetic on the shared array: an integer round trip would lose the address space
     // and turn every shared-memory access below into a generic LD/ST
@@ -310,10 +318,9 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
     const int num_kb = p.K / kTcKB;
     unsigned char* w_res = tiles + (size_t)S * stage_bytes;
     float* s_scale = reinterpret_cast<float*>(w_res + (p.w_resident ? (size_t)num_kb * 2 * w_bytes : 0));   // [K]
-    float* s_shift = s_scale + p.K;
-    float* s_bias = s_shift + p.K;                                                // [2 * N]
+    float* s_bias = s_scale + 4 * p.K;                                            // ([2 groups][scale K | shift K] above)                                                // [2 * N]
     float* s_estage = s_bias + 2 * p.N;                                           // [4 warps][32][36] epilogue staging
-    float* s_part = s_estage + 4 * 32 * 36;                                       // [4 warps][128 columns][2]
+    float* s_part = s_estage + (p.epi == TC_EPI_PLAIN ? 8 * 32 * 36 : 0);           // (the GRU epilogues do not stage)                                       // [4 warps][128 columns][2]
     __shared__ __align__(8) unsigned long long s_full[kTcMaxStages], s_ready[kTcMaxStages], s_empty[kTcMaxStages];
     __shared__ __align__(8) unsigned long long s_acc_full[2], s_acc_empty[2], s_w_full;
     __shared__ unsigned s_tmem_base;
@@ -329,10 +336,11 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a0) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < S; ++s) { tmbar_init(&s_full[s], 1); tmbar_init(&s_ready[s], kTcXform / 32); tmbar_init(&s_empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { tmbar_init(&s_acc_full[a], 1); tmbar_init(&s_acc_empty[a], 4); }
+        for (int s = 0; s < S; ++s) { tmbar_init(&s_full[s], 1); tmbar_init(&s_ready[s], kTcXform / 64); tmbar_init(&s_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { tmbar_init(&s_acc_full[a], 1); tmbar_init(&s_acc_empty[a], 8); }
         tmbar_init(&s_w_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -341,7 +349,7 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 10) {
-        for (int c = threadIdx.x - 320; c < p.N; c += 128) {
+        for (int c = threadIdx.x - 320; c < p.N; c += 256) {
             s_bias[c] = (p.bias != nullptr && c < p.cout) ? __ldg(p.bias + c) : 0.f;
             s_bias[p.N + c] = (p.bias2 != nullptr && c < p.cout) ? __ldg(p.bias2 + c) : 0.f;
         }
@@ -350,21 +358,9 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem = s_tmem_base;
-    if (p.dbg & 2) {   // isolated epilogue timing: nothing else runs on the SM
-        if (warp >= 10) {
-            for (int rep = 0; rep < 3; ++rep) {
-                if (clk && threadIdx.x == 320) g_tc_clock[44 + rep] = clock64();
-                if (clk && threadIdx.x == 320) g_tc_clock[40 + rep] = gtimer();
-                tc_epilogue(p, tmem, warp & 3, lane, blockIdx.x * kTcM, 0, s_bias, s_estage, s_part);
-            }
-            if (clk && threadIdx.x == 320) g_tc_clock[43] = gtimer();
-            if (clk && threadIdx.x == 320) g_tc_clock[47] = clock64();
-        }
-        __syncthreads();
-    }
 
     if (warp == 0) {
-        // ===== weight producer =====
+        // ===== TMA producer: raw activation boxes (and the weights) =====
         if (lane == 0) {
             if (p.w_resident) {   // the whole weight matrix (hi and lo) once per CTA
                 tmbar_expect_tx(&s_w_full, (unsigned)(num_kb * 2 * w_bytes));
@@ -372,13 +368,22 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
                     ttma_load_2d(w_res + (size_t)kb * 2 * w_bytes, &map_w_hi, &s_w_full, kb * kTcKB, 0);
                     ttma_load_2d(w_res + (size_t)kb * 2 * w_bytes + w_bytes, &map_w_lo, &s_w_full, kb * kTcKB, 0);
                 }
-            } else {
-                TcCursor cw;
-                for (int step = 0; step < total_steps; ++step, cw.next(num_kb, S)) {
-                    const int s = cw.s, kb = cw.kb;
-                    tmbar_wait(&s_empty[s], cw.phase ^ 1u);
-                    unsigned char* st = tiles + (size_t)s * stage_bytes;
-                    tmbar_expect_tx(&s_full[s], (unsigned)(2 * w_bytes));
+            }
+            const unsigned tx = (unsigned)(kTcABytes * (p.minmax ? 2 : 1) + (p.w_resident ? 0 : 2 * w_bytes));
+            TcCursor cw;
+            for (int step = 0; step < total_steps; ++step, cw.next(num_kb, S)) {
+                const int s = cw.s, kb = cw.kb;
+                const int row0 = (blockIdx.x + cw.ti * gridDim.x) * kTcM;
+                tmbar_wait(&s_empty[s], cw.phase ^ 1u);   // the MMAs that read this stage last time have retired
+                unsigned char* st = tiles + (size_t)s * stage_bytes;
+                tmbar_expect_tx(&s_full[s], tx);
+                // raw fp32 rows of the source this k-block belongs to land where the hi operand will be (the transform works
+                // in place); the min array of a (max, min) pair lands in the lo half
+                if (kb < p.seg_kb[0]) ttma_load_2d(st, &map_a0, &s_full[s], kb * kTcKB, row0);
+                else if (kb < p.seg_kb[0] + p.seg_kb[1]) ttma_load_2d(st, &map_a1, &s_full[s], (kb - p.seg_kb[0]) * kTcKB, row0);
+                else ttma_load_2d(st, &map_a2, &s_full[s], (kb - p.seg_kb[0] - p.seg_kb[1]) * kTcKB, row0);
+                if (p.minmax) ttma_load_2d(st + kTcABytes, &map_min, &s_full[s], kb * kTcKB, row0);
+                if (!p.w_resident) {
                     ttma_load_2d(st + w_off, &map_w_hi, &s_full[s], kb * kTcKB, 0);
                     ttma_load_2d(st + w_off + w_bytes, &map_w_lo, &s_full[s], kb * kTcKB, 0);
                 }
@@ -403,7 +408,7 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
                     const int s = cm.s;
                     const unsigned phase = cm.phase;
                     tmbar_wait(&s_ready[s], phase);               // transformed activations are in place
-                    if (!p.w_resident) tmbar_wait(&s_full[s], phase);   // streamed weight boxes have landed
+                    tmbar_wait(&s_full[s], phase);                // (already complete: the transform waited on it)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     unsigned char* st = tiles + (size_t)s * stage_bytes;
                     const unsigned long long a_hi = tumma_desc(st), a_lo = tumma_desc(st + kTcABytes);
@@ -426,73 +431,48 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
             }
         }
     } else if (warp < 10) {
-        // ===== activation loaders + transform =====
-        const int t = threadIdx.x - 64;   // 0..255: chunk c = t + 256*i, i < 4, of the 1024 16-byte chunks of a k-block
+        // ===== transform: raw fp32 box -> GroupNorm affine + activation -> tf32 hi/lo operand tiles, in place =====
+        // Two groups of four warps take alternate k-blocks, so the load -> math -> store -> fence chain of one step
+        // overlaps the next step's; each group keeps its own copy of the per-sample GroupNorm table.
+        const int grp = (warp - 2) >> 2;
+        const int t = (threadIdx.x - 64) & 127;   // chunk c = t + 128*i, i < 8, of the 1024 16-byte chunks of a k-block
+        float* g_scale = s_scale + grp * 2 * p.K;
+        float* g_shift = g_scale + p.K;
         const ActCoef iact = act_coef(p.in_act, p.in_slope);
-        // cp.async ring: thread t moves the same four 16-byte chunks of every k-block that it later transforms, so the
-        // only wait it needs is on its own copy groups; D k-blocks are in flight per thread (D = min(4, stages - 1))
-        const int D = min(kTcDepth, S - 1);
-        TcCursor ci, cp;   // issue / process positions
+        TcCursor cp;
         const int tiles_per_sample = p.pts_per_sample / kTcM;
-        int next_sample_tile = 0;   // first tile index (global) of the sample after cur_sample
-        auto issue = [&](int step) {
-            if (step < total_steps) {
-                const int ti = ci.ti, kb = ci.kb;
-                const int row0 = (blockIdx.x + ti * gridDim.x) * kTcM;
-                int seg = 0, kk = kb;   // which source tensor does this k-block come from?
-                if (kk >= p.seg_kb[0]) { kk -= p.seg_kb[0]; seg = 1; if (kk >= p.seg_kb[1]) { kk -= p.seg_kb[1]; seg = 2; } }
-                const float* src = p.src[seg];
-                const int ld = p.seg_kb[seg] * kTcKB;
-                const int s = ci.s;
-                tmbar_wait(&s_empty[s], ci.phase ^ 1u);   // the MMAs that read this stage last time have retired
-                const unsigned st = tsu32(tiles + (size_t)s * stage_bytes);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int c = t + i * kTcXform, r = c >> 3, lc = c & 7;
-                    const size_t off = (size_t)(row0 + r) * ld + kk * kTcKB + lc * 4;
-                    // K-major SWIZZLE_128B: 16-byte chunk lc of row r lives at chunk (lc ^ (r & 7)) of the row's 128 bytes
-                    const unsigned dst = st + (unsigned)(r * 128 + ((lc ^ (r & 7)) << 4));
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + off) : "memory");
-                    if (p.minmax) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)kTcABytes), "l"(p.src_min + off) : "memory");
-                }
-                ci.next(num_kb, S);
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");   // (an empty group past the end keeps the count uniform)
-        };
-        auto process = [&](int step) {
-            const int ti = cp.ti, kb = cp.kb;
-            const int s = cp.s;
-            if (p.in_stats != nullptr && kb == 0) {
-                const int tile = blockIdx.x + ti * gridDim.x;
-                if (tile >= next_sample_tile) {   // folded GroupNorm affine of every input channel of this sample
+        int table_first = -1, table_end = -1;   // tile range [first, end) of the sample whose table this group holds
+        if (grp == 1) cp.next(num_kb, S);
+        for (int step = grp; step < total_steps; step += 2) {
+            const int kb = cp.kb, s = cp.s;
+            if (p.in_stats != nullptr) {
+                const int tile = blockIdx.x + cp.ti * gridDim.x;
+                if (tile < table_first || tile >= table_end) {   // folded GroupNorm affine of every input channel of this sample
                     const int sample = tile / tiles_per_sample;
-                    next_sample_tile = (sample + 1) * tiles_per_sample;
-                    asm volatile("bar.sync 1, 256;" ::: "memory");   // everyone is done with the previous sample's table
-                    const int gsz = p.K / PVRAFT_GN_GROUPS;
-                    for (int k = t; k < p.K; k += kTcXform) {
+                    table_first = sample * tiles_per_sample;
+                    table_end = table_first + tiles_per_sample;
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // the group is done with the previous table
+                    const int gn_k = p.gn_kb * kTcKB, gsz = gn_k / PVRAFT_GN_GROUPS;
+                    for (int k = t; k < gn_k; k += 128) {
                         const GnAffine af = gn_affine(p.in_stats + (size_t)sample * 16 + (k / gsz) * 2, p.in_count, __ldg(p.in_gamma + k), __ldg(p.in_beta + k));
-                        s_scale[k] = af.scale;
-                        s_shift[k] = af.shift;
+                        g_scale[k] = af.scale;
+                        g_shift[k] = af.shift;
                     }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
                 }
             }
-            switch (D - 1) {   // all but the D-1 youngest copy groups of this thread have landed
-                case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-                case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-                case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-                default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-            }
+            tmbar_wait(&s_full[s], cp.phase);   // the raw box(es) of this k-block have landed
             unsigned char* st = tiles + (size_t)s * stage_bytes;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c = t + i * kTcXform, r = c >> 3, lc = c & 7;
+            for (int i = 0; i < 8; ++i) {
+                const int c = t + i * 128, r = c >> 3, lc = c & 7;
+                // K-major SWIZZLE_128B: 16-byte chunk lc of row r lives at chunk (lc ^ (r & 7)) of the row's 128 bytes
                 const int off = r * 128 + ((lc ^ (r & 7)) << 4);
                 float4 x = *reinterpret_cast<const float4*>(st + off);
-                if (p.in_stats != nullptr) {
+                if (kb < p.gn_kb) {
                     const int k = kb * kTcKB + lc * 4;
-                    const float4 sc = *reinterpret_cast<const float4*>(s_scale + k);
-                    const float4 sh = *reinterpret_cast<const float4*>(s_shift + k);
+                    const float4 sc = *reinterpret_cast<const float4*>(g_scale + k);
+                    const float4 sh = *reinterpret_cast<const float4*>(g_shift + k);
                     if (p.minmax) {
                         const float4 mn = *reinterpret_cast<const float4*>(st + kTcABytes + off);
                         x.x = sc.x < 0.f ? mn.x : x.x; x.y = sc.y < 0.f ? mn.y : x.y;
@@ -511,19 +491,15 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
             __syncwarp();
-            if (lane == 0) tmbar_arrive(&s_ready[s]);   // one arrival per loader warp
+            if (lane == 0) tmbar_arrive(&s_ready[s]);   // one arrival per warp of the group
             if (clk && t == 0 && step < 8) g_tc_clock[8 + step] = gtimer();
             cp.next(num_kb, S);
-        };
-        for (int d = 0; d < D; ++d) issue(d);
-        for (int step = 0; step < total_steps; ++step) {
-            process(step);
-            issue(step + D);
+            cp.next(num_kb, S);
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else {
         // ===== epilogue: TMEM -> registers -> global, one accumulator buffer behind the MMA =====
-        const int quad = warp & 3;   // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        const int quad = warp & 3;          // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        const int half = (warp - 10) >> 2;  // two warps per lane quadrant: 32-column chunks c0 = 32*half, +64, ...
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int acc = ti & 1;
             const unsigned acc_phase = (unsigned)(ti >> 1) & 1u;
@@ -531,7 +507,7 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
             tmbar_wait(&s_acc_full[acc], acc_phase);
             if (clk && threadIdx.x == 320 && ti < 4) g_tc_clock[24 + ti] = gtimer();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            tc_epilogue(p, tmem + (unsigned)acc * acc_cols, quad, lane, row0, row0 / p.pts_per_sample, s_bias, s_estage, s_part);
+            tc_epilogue(p, tmem + (unsigned)acc * acc_cols, quad, half, lane, row0, row0 / p.pts_per_sample, s_bias, s_estage, s_part);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) tmbar_arrive(&s_acc_empty[acc]);   // one arrival per epilogue warp
@@ -614,7 +590,8 @@ extern "C" int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream
         if (a->in[s]) K += a->in_channels[s];
     }
     if (K <= 0 || K > 512) return fail(PVRAFT_ERR_UNSUPPORTED, "tc_linear: K=%d", K);
-    if (a->in_stats && (K % PVRAFT_GN_GROUPS || !a->in_gamma || !a->in_beta || a->in[1])) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: GroupNorm prologue needs a single source with K %% 8 == 0");
+    if (a->in_stats && (a->in_channels[0] % PVRAFT_GN_GROUPS || !a->in_gamma || !a->in_beta)) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: GroupNorm prologue needs gamma, beta and in_channels[0] %% 8 == 0");
+    if (a->tail && (a->epilogue != TC_EPI_PLAIN || a->cout + 3 != a->n_pad || a->n_pad % 32 || a->residual || a->out_stats)) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: a tail needs the plain epilogue and cout + 3 == n_pad (multiple of 32)");
     if (a->in_min && !a->in_stats) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: in_min needs the GroupNorm prologue");
     if (a->out_stats && (a->epilogue != TC_EPI_PLAIN || a->cout % PVRAFT_GN_GROUPS || (a->cout / PVRAFT_GN_GROUPS) % 4)) return fail(PVRAFT_ERR_UNSUPPORTED, "tc_linear: out_stats needs a GroupNorm group size that is a multiple of 4 (cout=%d)", a->cout);
     if (a->epilogue != TC_EPI_PLAIN && (a->cout != 64 || !a->h || !a->bias)) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: GRU epilogues need cout=64, h and bias");
@@ -634,18 +611,30 @@ extern "C" int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream
         p.seg_kb[s] = a->in[s] ? a->in_channels[s] / kTcKB : 0;
     }
     p.src_min = a->in_min;
+    p.gn_kb = a->in_stats ? a->in_channels[0] / kTcKB : 0;
+    p.tail = a->tail;
+    p.out_ld = a->tail ? a->cout + 3 : a->cout;
     if ((rc = tc_make_map(&mw_hi, a->w_hi, a->n_pad, K, K, a->n_pad)) || (rc = tc_make_map(&mw_lo, a->w_lo, a->n_pad, K, K, a->n_pad))) return rc;
+    CUtensorMap ma[3], mmin;
+    for (int s = 0; s < 3; ++s) {   // unused slots repeat source 0 (a tensor map must be valid even if never dereferenced)
+        const int q = a->in[s] ? s : 0;
+        if ((rc = tc_make_map(&ma[s], a->in[q], M, a->in_channels[q], a->in_channels[q], kTcM))) return rc;
+    }
+    if ((rc = tc_make_map(&mmin, a->in_min ? a->in_min : a->in[0], M, a->in_channels[0], a->in_channels[0], kTcM))) return rc;
     const size_t a_stage = (size_t)2 * kTcABytes;
     const size_t w_all = (size_t)(K / kTcKB) * 2 * a->n_pad * kTcKB * 4;          // hi + lo of the whole weight matrix
-    const size_t fixed = (size_t)(2 * K + 2 * a->n_pad + 4 * 32 * 36 + 4 * 128 * 2) * sizeof(float) + 1024 + 64;
+    const size_t fixed = (size_t)(4 * K + 2 * a->n_pad + (a->epilogue == TC_EPI_PLAIN ? 8 * 32 * 36 : 0) + 4 * 128 * 2) * sizeof(float) + 1024 + 64;
     const size_t budget = (size_t)kSmemBudget - 2048 /* static barriers */ - fixed;
-    // weights stay resident in shared memory whenever they leave room for >= 2 activation stages: re-streaming the
-    // same few KB per tile from every SM hot-spots a handful of L2 slices
-    p.w_resident = w_all + 2 * a_stage <= budget ? 1 : 0;
-    if (const char* e = getenv("PVRAFT_TC_WRES")) p.w_resident = (atoi(e) != 0 && w_all + a_stage <= budget) ? 1 : 0;
-    const size_t stage = a_stage + (p.w_resident ? 0 : (size_t)2 * a->n_pad * kTcKB * 4);
-    int stages = (int)((budget - (p.w_resident ? w_all : 0)) / stage);
+    // Weights stay resident in shared memory when that still leaves a ring of >= 3 activation stages (re-streaming the
+    // same few KB per tile from every SM hot-spots a handful of L2 slices); otherwise they travel with the k-blocks.
+    const size_t w_kb = (size_t)2 * a->n_pad * kTcKB * 4;
+    const int stages_res = w_all < budget ? (int)((budget - w_all) / a_stage) : 0;
+    const int stages_str = (int)(budget / (a_stage + w_kb));
+    p.w_resident = (stages_res >= 3 || stages_res >= stages_str) ? 1 : 0;
+    if (const char* e = getenv("PVRAFT_TC_WRES")) p.w_resident = (atoi(e) != 0 && stages_res >= 1) ? 1 : 0;
+    int stages = p.w_resident ? stages_res : stages_str;
     stages = stages < 1 ? 1 : (stages > kTcMaxStages ? kTcMaxStages : stages);
+    const size_t stage = a_stage + (p.w_resident ? 0 : w_kb);
     if (const char* e = getenv("PVRAFT_TC_STAGES")) { const int v = atoi(e); if (v >= 1 && v <= stages) stages = v; }
     p.stages = stages;
     if (const char* e = getenv("PVRAFT_TC_DBG")) p.dbg = atoi(e);
@@ -653,6 +642,6 @@ extern "C" int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream
     if ((rc = opt_in_smem(k_tc_linear, smem))) return rc;
     const long long n_tiles = (M + kTcM - 1) / kTcM;
     const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
-    k_tc_linear<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(mw_hi, mw_lo, p);
+    k_tc_linear<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(mw_hi, mw_lo, ma[0], ma[1], ma[2], mmin, p);
     return check_launch("tc_linear");
 }

@@ -113,20 +113,22 @@ _TC_WEIGHTS = {}
 TC_PLAIN, TC_GRU_ZR, TC_GRU_Q = 0, 1, 2
 
 
-def tc_weights(weights, col0=0, cols=None, k_pad=None):
+def tc_weights(weights, col0=0, cols=None, k_pad=None, kcat=False):
     """tf32 hi/lo split of a (stack of) [cout, cin(,1,1)] weight(s) -> (hi, lo) [n_pad, k_pad], cached per parameter
     version (inference weights are static, so this runs once)."""
     if torch.is_tensor(weights):
         weights = (weights,)
     # keyed by the identity of the source tensor OBJECTS (validated through weak references and version counters):
     # a data_ptr key would go stale when the allocator hands a freed weight's address to a new tensor
-    key = tuple(id(w) for w in weights) + (col0, cols, k_pad)
+    key = tuple(id(w) for w in weights) + (col0, cols, k_pad, kcat)
     hit = _TC_WEIGHTS.get(key)
     if hit is not None:
         refs, versions, ptrs, result = hit
         if all(r() is w and w._version == v and w.data_ptr() == p for r, w, v, p in zip(refs, weights, versions, ptrs)):
             return result
     mats = [w.detach().reshape(w.shape[0], -1) for w in weights]
+    if kcat:   # [W_a | W_b | ...] along K: one GEMM over concatenated sources adds the layers' outputs
+        mats = [torch.cat(mats, 1).contiguous()]
     ld = mats[0].shape[1]
     ncols = ld - col0 if cols is None else cols
     kp = (ncols + 31) // 32 * 32 if k_pad is None else k_pad
@@ -147,6 +149,26 @@ def tc_weights(weights, col0=0, cols=None, k_pad=None):
     return result
 
 
+_DERIVED = {}
+
+
+def derived(tensors, tag, fn):
+    """Cache of small host- or device-side values derived from parameters (a bias sum, a PReLU slope read back once);
+    keyed by parameter identity, re-derived when a parameter's version or storage changes."""
+    key = tuple(id(t) for t in tensors) + (tag,)
+    hit = _DERIVED.get(key)
+    if hit is not None:
+        refs, versions, ptrs, value = hit
+        if all(r() is t and t._version == v and t.data_ptr() == p for r, t, v, p in zip(refs, tensors, versions, ptrs)):
+            return value
+    value = fn(*tensors)
+    if len(_DERIVED) > 512:
+        _DERIVED.clear()
+    _DERIVED[key] = (tuple(weakref.ref(t) for t in tensors), tuple(t._version for t in tensors),
+                     tuple(t.data_ptr() for t in tensors), value)
+    return value
+
+
 def tc_supported(n_points, *channels):
     """The tcgen05 layer needs 128-point tiles that do not straddle samples and 32-channel k-blocks."""
     return n_points % 128 == 0 and all(c % 32 == 0 for c in channels)
@@ -154,14 +176,15 @@ def tc_supported(n_points, *channels):
 
 def tc_linear(sources, w, bias=None, *, in_min=None, in_stats=None, in_gamma=None, in_beta=None, in_count=0.0,
               in_act=ACT_NONE, in_slope=0.0, out_act=ACT_NONE, residual=None, out=None, out_stats=None, epilogue=TC_PLAIN,
-              bias2=None, out2=None, h=None, z=None, cout=None):
-    """Fused layer on the tcgen05 tensor cores.  sources: list of [B,N,C_i] tensors concatenated along K;
-    w = (hi, lo, n_pad, rows) from tc_weights()."""
+              bias2=None, out2=None, h=None, z=None, cout=None, tail=None):
+    """Fused layer on the tcgen05 tensor cores.  sources: list of [B,N,C_i] tensors concatenated along K (the
+    GroupNorm prologue applies to sources[0]); w = (hi, lo, n_pad, rows) from tc_weights(); tail [B,N,3] fills the
+    output columns cout..cout+2."""
     hi, lo, n_pad, rows = w
     b, n, _ = sources[0].shape
     cout = rows if cout is None else cout
     if out is None:
-        out = torch.empty(b, n, cout, dtype=torch.float32, device=sources[0].device)
+        out = torch.empty(b, n, cout + (3 if tail is not None else 0), dtype=torch.float32, device=sources[0].device)
     a = _lib.TcLinearArgs()
     for i, src in enumerate(sources):
         a.in_[i] = _p(src)
@@ -172,6 +195,7 @@ def tc_linear(sources, w, bias=None, *, in_min=None, in_stats=None, in_gamma=Non
     a.bias, a.bias2, a.out_act, a.residual = _p(bias), _p(bias2), out_act, _p(residual)
     a.out, a.out2, a.h, a.z = _p(out), _p(out2), _p(h), _p(z)
     a.out_stats, a.epilogue, a.B, a.N = _p(out_stats, torch.float64), epilogue, b, n
+    a.tail = _p(tail)
     _count(lib().pvraft_tc_linear_fwd(C.byref(a), _stream()), 'tc_linear')
     return out
 
@@ -194,6 +218,10 @@ def transpose(x):
 
 def corr_feature(args):
     _count(lib().pvraft_corr_feature_fwd(C.byref(args), _stream()), 'corr_feature')
+
+
+def knn_branch(args):
+    _count(lib().pvraft_knn_branch_fwd(C.byref(args), _stream()), 'knn_branch')
 
 
 def gru(args):

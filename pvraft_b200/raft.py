@@ -45,15 +45,19 @@ class _RaftBase(nn.Module):
         flow = torch.zeros_like(xyz1)
         preds = []
         me = self.update_block.motion_encoder
+        use_tc = ops.tc_supported(n)
         for _ in range(num_iters):
-            motion = torch.empty(b, n, 64, dtype=torch.float32, device=xyz1.device)
+            if use_tc:
+                _, motion = self.corr_block.feature_motion_tc(coords2, flow, me)          # :42 + update.py:83
+            else:
+                motion = torch.empty(b, n, 64, dtype=torch.float32, device=xyz1.device)
 
-            def attach(a, keep, flow=flow, motion=motion):
-                me.fill(a, flow)
-                a.motion = ops._p(motion)
-                keep.append(motion)
+                def attach(a, keep, flow=flow, motion=motion):
+                    me.fill(a, flow)
+                    a.motion = ops._p(motion)
+                    keep.append(motion)
 
-            _, keep = self.corr_block.feature_point_major(coords2, motion_args=attach)   # :42 + update.py:83
+                _, keep = self.corr_block.feature_point_major(coords2, motion_args=attach)   # :42 + update.py:83
             new_flow = torch.empty_like(xyz1)
             net, _ = self.update_block.forward_pm(net, inp, motion, graph_context, coords1=xyz1, coords2=coords2,
                                                   coords2_out=coords2, flow_out=new_flow)   # :44-46

@@ -251,6 +251,7 @@ def golden_graph(arr, dev):
 
 @pytest.mark.parametrize('fixture,refine', [('small_rsf_refine.npz', True), ('oddscale_rsf.npz', False)])
 def test_modules_teacher_forced_vs_reference(dev, fixture, refine):
+    from pvraft_b200 import ops
     arr, W, m = golden_model(fixture, dev, refine)
     install_golden_state(m, arr, dev)
     g = golden_graph(arr, dev)
@@ -274,6 +275,11 @@ def test_modules_teacher_forced_vs_reference(dev, fixture, refine):
             gcorr = arr[f'it{it}/corr'].to(dev)
             mot = m.update_block.motion_encoder(flow, gcorr)
             assert rel_err(mot.cpu(), arr[f'it{it}/motion']) < TOL
+            if ops.tc_supported(coords.shape[1]):   # the loop's path: feature head + MotionEncoder on the tensor cores
+                corr_pm, mot_pm = m.corr_block.feature_motion_tc(coords, flow.contiguous(), m.update_block.motion_encoder)
+                assert rel_err(corr_pm.transpose(1, 2).cpu(), arr[f'it{it}/corr']) < TOL
+                assert rel_err(mot_pm.transpose(1, 2).cpu(), arr[f'it{it}/motion']) < 2 * TOL   # (its input is the computed corr)
+                assert torch.equal(mot_pm[..., 61:], flow)
             net2, delta = m.update_block(net, inp, gcorr, flow, g)                 # UpdateBlock.forward
             assert rel_err(net2.cpu(), arr[f'it{it}/net']) < TOL
             assert rel_err(delta.cpu(), arr[f'it{it}/delta']) < 5e-5

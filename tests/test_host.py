@@ -26,7 +26,8 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), 'ctypes binding and header disagree'
     lib = _lib.lib()
     assert lib.pvraft_version() == 100
-    for which, struct in enumerate([_lib.LinearArgs, _lib.CorrFeatArgs, _lib.GruArgs, _lib.FlowOutArgs, _lib.TcLinearArgs]):
+    for which, struct in enumerate([_lib.LinearArgs, _lib.CorrFeatArgs, _lib.GruArgs, _lib.FlowOutArgs, _lib.TcLinearArgs,
+                                    _lib.KnnBranchArgs]):
         assert lib.pvraft_sizeof(which) == ctypes.sizeof(struct), f'struct {struct.__name__} layout drifted'
 
 

@@ -27,7 +27,7 @@ def run(cin, cout, stats, reps=30, srcs=1):
     t = s.elapsed_time(e) * 1e3 / reps
     byt = b * n * (cin + cout) * 4
     print(json.dumps(dict(cin=cin, cout=cout, stats=stats, srcs=srcs, us=round(t, 1), GBps=round(byt / t / 1e3), TFLOPs=round(2 * b * n * cin * cout * 3 / t / 1e6, 1))))
-cases = [(64, 64, False, 1), (192, 128, False, 3)] if os.environ.get('PVRAFT_TC_DBG') else None
+cases = [(64, 64, False, 1), (192, 64, False, 3), (64, 128, False, 1), (256, 64, False, 1)] if os.environ.get('PVRAFT_TC_DBG') else None
 for cin, cout, stats, srcs in cases or [(32, 64, False, 1), (64, 64, False, 1), (64, 64, True, 1), (128, 64, False, 1), (192, 64, False, 3), (192, 128, False, 3),
                                (96, 128, True, 1), (64, 32, False, 1), (64, 128, False, 1), (256, 64, False, 1)]:
     run(cin, cout, stats, srcs=srcs)
