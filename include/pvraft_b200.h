@@ -160,7 +160,10 @@ PVRAFT_API int pvraft_linear_fwd(const pvraft_linear_args* a, void* stream);
 typedef enum pvraft_tc_epilogue {
     PVRAFT_TC_PLAIN = 0,   /* out = act(acc + bias) (+ residual), optional output statistics                  */
     PVRAFT_TC_GRU_ZR = 1,  /* acc = [z|r] pre-activations (n_pad = 128): out = sigmoid(z), out2 = sigmoid(r) * h */
-    PVRAFT_TC_GRU_Q = 2    /* acc = q pre-activation: out = (1 - z) * h + z * tanh(acc + bias)                  */
+    PVRAFT_TC_GRU_Q = 2,   /* acc = q pre-activation: out = (1 - z) * h + z * tanh(acc + bias)                  */
+    PVRAFT_TC_FLOW = 3     /* FlowHead tail (model/update.py:72) + RAFT update (model/RAFTSceneFlow.py:45-46), cout = 64:
+                              out[B,N,3] = delta = w3 . relu(acc + bias) + b3; coords2_out = coords2 + delta;
+                              flow_out = coords2_out - coords1 (the last two optional)                         */
 } pvraft_tc_epilogue;
 
 typedef struct pvraft_tc_linear_args {
@@ -189,6 +192,12 @@ typedef struct pvraft_tc_linear_args {
     int B, N;
     const float* tail;      /* PLAIN, or NULL: [B,N,3] copied into output columns cout..cout+2 (out row stride cout+3 = n_pad):
                                the MotionEncoder's `cat([out, flow])`, model/update.py:20 */
+    const float* w3;        /* FLOW: flow_head.out_conv.2.weight [3,64] */
+    const float* b3;        /* FLOW: flow_head.out_conv.2.bias [3] */
+    const float* coords1;   /* FLOW: [B,N,3] or NULL */
+    const float* coords2;   /* FLOW: [B,N,3] or NULL */
+    float* coords2_out;     /* FLOW: [B,N,3] or NULL (may alias coords2) */
+    float* flow_out;        /* FLOW: [B,N,3] or NULL */
 } pvraft_tc_linear_args;
 
 PVRAFT_API int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream);

@@ -103,6 +103,98 @@ __global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge(const float* __re
     }
 }
 
+// C % 64 == 0 (the flow head's SetConv, 64 channels, runs every RAFT iteration): lane l owns the adjacent channel pairs
+// (2l, 2l+1) + 64q, so a neighbour row is one 8-byte load per lane and pair, and the per-edge scalars (neighbour id, edge
+// vector) are read back as ONE broadcast 16-byte shared-memory load instead of four shuffles.
+template <int PAIRS>
+__global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge_pairs(const float* __restrict__ fc1p, const int32_t* __restrict__ nbr,
+                                                                     const float* __restrict__ edge_feats, const float* __restrict__ w_fc1,
+                                                                     int cin, int B, int N, int C, float* __restrict__ ymax,
+                                                                     float* __restrict__ ymin, double* __restrict__ stats) {
+    __shared__ double s_part[kEdgeThreads / 32][128][2];
+    __shared__ __align__(16) float4 s_edge[kEdgeThreads / 32][32];   // (neighbour id bits, ex, ey, ez) of the warp's point
+    const int lane = lane_id(), w = warp_id(), nwarps = kEdgeThreads / 32;
+    const int ld = cin + 3;
+    float2 wx[PAIRS], wy[PAIRS], wz[PAIRS];
+#pragma unroll
+    for (int q = 0; q < PAIRS; ++q) {
+        const int c = 2 * lane + 64 * q;
+        wx[q] = make_float2(__ldg(w_fc1 + (size_t)c * ld + cin + 0), __ldg(w_fc1 + (size_t)(c + 1) * ld + cin + 0));
+        wy[q] = make_float2(__ldg(w_fc1 + (size_t)c * ld + cin + 1), __ldg(w_fc1 + (size_t)(c + 1) * ld + cin + 1));
+        wz[q] = make_float2(__ldg(w_fc1 + (size_t)c * ld + cin + 2), __ldg(w_fc1 + (size_t)(c + 1) * ld + cin + 2));
+    }
+    const long long total = (long long)B * N;
+    long long pt_begin, pt_end;
+    split_range(total, gridDim.x, blockIdx.x, pt_begin, pt_end);
+    long long seg = pt_begin;
+    while (seg < pt_end) {
+        const int b = (int)(seg / N);
+        long long seg_end = (long long)(b + 1) * N;
+        if (seg_end > pt_end) seg_end = pt_end;
+        double dS[PAIRS][2], dSS[PAIRS][2];
+#pragma unroll
+        for (int q = 0; q < PAIRS; ++q) { dS[q][0] = dS[q][1] = 0.0; dSS[q][0] = dSS[q][1] = 0.0; }
+        const float* P = fc1p + (size_t)b * N * C + 2 * lane;
+        for (long long pt = seg + w; pt < seg_end; pt += nwarps) {
+            const int i = (int)(pt - (long long)b * N);
+            // lane e parks neighbour e: id and edge feature x_j - x_i (graph.edge_feats, gconv.py:66)
+            const float* ef = edge_feats + ((size_t)pt * 32 + lane) * 3;
+            __syncwarp();
+            s_edge[w][lane] = make_float4(__int_as_float(__ldg(nbr + pt * 32 + lane) * C), __ldg(ef), __ldg(ef + 1), __ldg(ef + 2));
+            __syncwarp();
+            float2 pi[PAIRS], mx[PAIRS], mn[PAIRS], s1[PAIRS], s2[PAIRS];
+#pragma unroll
+            for (int q = 0; q < PAIRS; ++q) {
+                pi[q] = __ldg(reinterpret_cast<const float2*>(P + (size_t)i * C + 64 * q));
+                mx[q] = make_float2(-INFINITY, -INFINITY); mn[q] = make_float2(INFINITY, INFINITY);
+                s1[q] = make_float2(0.f, 0.f); s2[q] = make_float2(0.f, 0.f);
+            }
+#pragma unroll 8
+            for (int e = 0; e < 32; ++e) {
+                const float4 ed = s_edge[w][e];
+                const float* row = P + __float_as_int(ed.x);
+#pragma unroll
+                for (int q = 0; q < PAIRS; ++q) {
+                    const float2 pj = __ldg(reinterpret_cast<const float2*>(row + 64 * q));
+                    const float y0 = (pj.x - pi[q].x) + fmaf(wz[q].x, ed.w, fmaf(wy[q].x, ed.z, wx[q].x * ed.y));
+                    const float y1 = (pj.y - pi[q].y) + fmaf(wz[q].y, ed.w, fmaf(wy[q].y, ed.z, wx[q].y * ed.y));
+                    mx[q].x = fmaxf(mx[q].x, y0); mx[q].y = fmaxf(mx[q].y, y1);
+                    mn[q].x = fminf(mn[q].x, y0); mn[q].y = fminf(mn[q].y, y1);
+                    s1[q].x += y0; s1[q].y += y1;
+                    s2[q].x = fmaf(y0, y0, s2[q].x); s2[q].y = fmaf(y1, y1, s2[q].y);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < PAIRS; ++q) {
+                const size_t o = (size_t)pt * C + 2 * lane + 64 * q;
+                *reinterpret_cast<float2*>(ymax + o) = mx[q];
+                *reinterpret_cast<float2*>(ymin + o) = mn[q];
+                dS[q][0] += (double)s1[q].x; dS[q][1] += (double)s1[q].y;
+                dSS[q][0] += (double)s2[q].x; dSS[q][1] += (double)s2[q].y;
+            }
+        }
+        // block reduction of the per-channel partials -> per-group sums -> one atomic per (group, moment)
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PAIRS; ++q) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                s_part[w][2 * lane + 64 * q + h][0] = dS[q][h];
+                s_part[w][2 * lane + 64 * q + h][1] = dSS[q][h];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 16) {
+            const int g = threadIdx.x >> 1, m = threadIdx.x & 1, gsz = C / PVRAFT_GN_GROUPS;
+            double acc = 0.0;
+            for (int c = g * gsz; c < (g + 1) * gsz; ++c)
+                for (int ww = 0; ww < nwarps; ++ww) acc += s_part[ww][c][m];
+            if (acc != 0.0) atomicAdd(stats + (size_t)b * 16 + threadIdx.x, acc);
+        }
+        seg = seg_end;
+    }
+}
+
 }  // namespace pvraft
 
 using namespace pvraft;
@@ -119,6 +211,14 @@ extern "C" int pvraft_setconv_edge_fwd(const float* fc1p, const int32_t* nbr, co
     const int grid = (int)(g < 1 ? 1 : g);
     cudaStream_t st = (cudaStream_t)stream;
     const int slots = (C + 31) / 32;
+    if (C == 64) {
+        k_setconv_edge_pairs<1><<<grid, kEdgeThreads, 0, st>>>(fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats);
+        return check_launch("setconv_edge");
+    }
+    if (C == 128) {
+        k_setconv_edge_pairs<2><<<grid, kEdgeThreads, 0, st>>>(fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats);
+        return check_launch("setconv_edge");
+    }
     switch (slots) {
         case 1: k_setconv_edge<1><<<grid, kEdgeThreads, 0, st>>>(fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats); break;
         case 2: k_setconv_edge<2><<<grid, kEdgeThreads, 0, st>>>(fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats); break;

@@ -29,7 +29,7 @@ constexpr int kTcMaxStages = 6;
 __device__ unsigned long long g_tc_clock[64];   // debug timeline of CTA 0 (env PVRAFT_TC_DBG=1)
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
-enum TcEpilogue { TC_EPI_PLAIN = 0, TC_EPI_GRU_ZR = 1, TC_EPI_GRU_Q = 2 };
+enum TcEpilogue { TC_EPI_PLAIN = 0, TC_EPI_GRU_ZR = 1, TC_EPI_GRU_Q = 2, TC_EPI_FLOW = 3 };
 
 struct TcParams {
     // prologue (per input channel, per sample): x = act(raw * scale + shift); raw = max or min input by sign(scale)
@@ -61,6 +61,8 @@ struct TcParams {
     int gn_kb;                // k-blocks (from the start: source 0) that go through the GroupNorm prologue
     int out_ld;               // row stride of `out` in floats (cout, or cout + 3 with a tail)
     const float* tail;        // [M,3] copied into output columns cout..cout+2, or nullptr
+    const float *w3, *b3, *coords1, *coords2;   // FLOW epilogue
+    float *coords2_out, *flow_out;
 };
 
 __device__ __forceinline__ unsigned tsu32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -255,6 +257,44 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
                 }
             }
         }
+    } else if (p.epi == TC_EPI_FLOW) {
+        // y = relu(acc + b) (flow_head.out_conv.0/1); delta = w3 . y + b3 (out_conv.2); RAFT update of the coordinates.
+        // The two warps of a lane quadrant hold 32 of the 64 columns each: half 1 parks its partial dot products.
+        const float* s_w3 = s_part + 512;   // [3][64], staged at kernel start; s_part[0..511] = [128 rows][4] exchange
+        unsigned v[32];
+        const int c0 = half * 32;
+        tmem_ld32(tl + (unsigned)c0, v);
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0 + q * 4);
+            const float4 wa = *reinterpret_cast<const float4*>(s_w3 + 0 * 64 + c0 + q * 4);
+            const float4 wb = *reinterpret_cast<const float4*>(s_w3 + 1 * 64 + c0 + q * 4);
+            const float4 wc = *reinterpret_cast<const float4*>(s_w3 + 2 * 64 + c0 + q * 4);
+            const float y0 = fmaxf(__uint_as_float(v[q * 4 + 0]) + bv.x, 0.f), y1 = fmaxf(__uint_as_float(v[q * 4 + 1]) + bv.y, 0.f);
+            const float y2 = fmaxf(__uint_as_float(v[q * 4 + 2]) + bv.z, 0.f), y3 = fmaxf(__uint_as_float(v[q * 4 + 3]) + bv.w, 0.f);
+            d0 = fmaf(wa.w, y3, fmaf(wa.z, y2, fmaf(wa.y, y1, fmaf(wa.x, y0, d0))));
+            d1 = fmaf(wb.w, y3, fmaf(wb.z, y2, fmaf(wb.y, y1, fmaf(wb.x, y0, d1))));
+            d2 = fmaf(wc.w, y3, fmaf(wc.z, y2, fmaf(wc.y, y1, fmaf(wc.x, y0, d2))));
+        }
+        float* xch = s_part + (size_t)(quad * 32 + lane) * 4;
+        if (half == 1) *reinterpret_cast<float4*>(xch) = make_float4(d0, d1, d2, 0.f);
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (half == 0) {
+            const float4 o = *reinterpret_cast<const float4*>(xch);
+            const float dd[3] = {(d0 + o.x) + s_bias[p.N + 0], (d1 + o.y) + s_bias[p.N + 1], (d2 + o.z) + s_bias[p.N + 2]};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const size_t g = (size_t)row * 3 + k;
+                p.out[g] = dd[k];
+                if (p.coords2_out != nullptr) {
+                    const float c2 = p.coords2[g] + dd[k];   // RAFTSceneFlow.py:45
+                    p.coords2_out[g] = c2;
+                    if (p.flow_out != nullptr) p.flow_out[g] = c2 - __ldg(p.coords1 + g);   // RAFTSceneFlow.py:46
+                }
+            }
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");   // the exchange buffer is free for the next tile
     } else {
         // q = tanh(acc + b); h' = (1 - z) h + z q   (model/update.py:37-39)
         for (int c0 = half * 32; c0 < 64; c0 += 64) {
@@ -352,6 +392,10 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
         for (int c = threadIdx.x - 320; c < p.N; c += 256) {
             s_bias[c] = (p.bias != nullptr && c < p.cout) ? __ldg(p.bias + c) : 0.f;
             s_bias[p.N + c] = (p.bias2 != nullptr && c < p.cout) ? __ldg(p.bias2 + c) : 0.f;
+        }
+        if (p.epi == TC_EPI_FLOW) {   // out_conv.2: weights behind the exchange buffer, bias in the bias2 slots
+            for (int i = threadIdx.x - 320; i < 192; i += 256) s_part[512 + i] = __ldg(p.w3 + i);
+            if (threadIdx.x - 320 < 3) s_bias[p.N + threadIdx.x - 320] = __ldg(p.b3 + threadIdx.x - 320);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -594,7 +638,9 @@ extern "C" int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream
     if (a->tail && (a->epilogue != TC_EPI_PLAIN || a->cout + 3 != a->n_pad || a->n_pad % 32 || a->residual || a->out_stats)) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: a tail needs the plain epilogue and cout + 3 == n_pad (multiple of 32)");
     if (a->in_min && !a->in_stats) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: in_min needs the GroupNorm prologue");
     if (a->out_stats && (a->epilogue != TC_EPI_PLAIN || a->cout % PVRAFT_GN_GROUPS || (a->cout / PVRAFT_GN_GROUPS) % 4)) return fail(PVRAFT_ERR_UNSUPPORTED, "tc_linear: out_stats needs a GroupNorm group size that is a multiple of 4 (cout=%d)", a->cout);
-    if (a->epilogue != TC_EPI_PLAIN && (a->cout != 64 || !a->h || !a->bias)) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: GRU epilogues need cout=64, h and bias");
+    if (a->epilogue < TC_EPI_PLAIN || a->epilogue > TC_EPI_FLOW) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: unknown epilogue %d", a->epilogue);
+    if ((a->epilogue == TC_EPI_GRU_ZR || a->epilogue == TC_EPI_GRU_Q) && (a->cout != 64 || !a->h || !a->bias)) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: GRU epilogues need cout=64, h and bias");
+    if (a->epilogue == TC_EPI_FLOW && (a->cout != 64 || a->n_pad != 64 || !a->bias || !a->w3 || !a->b3 || (a->coords2_out && !a->coords2) || (a->flow_out && (!a->coords2_out || !a->coords1)))) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: flow epilogue needs cout = n_pad = 64, bias, w3, b3 and consistent coordinate pointers");
     if (a->epilogue == TC_EPI_GRU_ZR && (a->n_pad != 128 || !a->bias2 || !a->out2)) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: GRU zr epilogue needs n_pad=128, bias2, out2");
     if (a->epilogue == TC_EPI_GRU_Q && (a->n_pad != 64 || !a->z)) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: GRU q epilogue needs n_pad=64 and z");
     const long long M = (long long)a->B * a->N;
@@ -613,6 +659,7 @@ extern "C" int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream
     p.src_min = a->in_min;
     p.gn_kb = a->in_stats ? a->in_channels[0] / kTcKB : 0;
     p.tail = a->tail;
+    p.w3 = a->w3; p.b3 = a->b3; p.coords1 = a->coords1; p.coords2 = a->coords2; p.coords2_out = a->coords2_out; p.flow_out = a->flow_out;
     p.out_ld = a->tail ? a->cout + 3 : a->cout;
     if ((rc = tc_make_map(&mw_hi, a->w_hi, a->n_pad, K, K, a->n_pad)) || (rc = tc_make_map(&mw_lo, a->w_lo, a->n_pad, K, K, a->n_pad))) return rc;
     CUtensorMap ma[3], mmin;

@@ -110,7 +110,7 @@ def linear(x, weight, bias=None, *, cin=None, w_ld=0, w_cin=0, in_mode=IN_PLAIN,
 
 
 _TC_WEIGHTS = {}
-TC_PLAIN, TC_GRU_ZR, TC_GRU_Q = 0, 1, 2
+TC_PLAIN, TC_GRU_ZR, TC_GRU_Q, TC_FLOW = 0, 1, 2, 3
 
 
 def tc_weights(weights, col0=0, cols=None, k_pad=None, kcat=False):
@@ -176,7 +176,8 @@ def tc_supported(n_points, *channels):
 
 def tc_linear(sources, w, bias=None, *, in_min=None, in_stats=None, in_gamma=None, in_beta=None, in_count=0.0,
               in_act=ACT_NONE, in_slope=0.0, out_act=ACT_NONE, residual=None, out=None, out_stats=None, epilogue=TC_PLAIN,
-              bias2=None, out2=None, h=None, z=None, cout=None, tail=None):
+              bias2=None, out2=None, h=None, z=None, cout=None, tail=None, w3=None, b3=None, coords1=None, coords2=None,
+              coords2_out=None, flow_out=None):
     """Fused layer on the tcgen05 tensor cores.  sources: list of [B,N,C_i] tensors concatenated along K (the
     GroupNorm prologue applies to sources[0]); w = (hi, lo, n_pad, rows) from tc_weights(); tail [B,N,3] fills the
     output columns cout..cout+2."""
@@ -196,6 +197,8 @@ def tc_linear(sources, w, bias=None, *, in_min=None, in_stats=None, in_gamma=Non
     a.out, a.out2, a.h, a.z = _p(out), _p(out2), _p(h), _p(z)
     a.out_stats, a.epilogue, a.B, a.N = _p(out_stats, torch.float64), epilogue, b, n
     a.tail = _p(tail)
+    a.w3, a.b3, a.coords1, a.coords2 = _p(w3), _p(b3), _p(coords1), _p(coords2)
+    a.coords2_out, a.flow_out = _p(coords2_out), _p(flow_out)
     _count(lib().pvraft_tc_linear_fwd(C.byref(a), _stream()), 'tc_linear')
     return out
 

@@ -113,6 +113,23 @@ class FlowHead(nn.Module):
         d = self.setconv.forward_deferred(net, graph)
         delta = torch.empty(b, n, 3, dtype=torch.float32, device=net.device)
         oc = self.out_conv
+        if ops.tc_supported(n):
+            # tcgen05, one launch: out_conv.0 on [setconv(x), conv1(x)] (update.py:68-71) is linear in x through conv1, so
+            # conv1 is folded into the second half of its weight: W [a3 | W_b W_c1] with bias W_b b_c1 + b_o0 (products in
+            # float64, rounded once).  Prologue: a3 = lrelu(GN3(z3)); epilogue: ReLU, out_conv.2 and the RAFT update
+            # (update.py:72, RAFTSceneFlow.py:45-46).
+            def fold(w_o0, w_c1, b_c1, b_o0):
+                wo = w_o0.detach().reshape(64, 128).double()
+                wc, bc = w_c1.detach().reshape(64, 64).double(), b_c1.detach().double()
+                w = torch.cat([wo[:, :64], wo[:, 64:] @ wc], 1).float().contiguous()
+                return w, (wo[:, 64:] @ bc + b_o0.detach().double()).float().contiguous()
+
+            w_eff, b_eff = ops.derived((oc[0].weight, self.conv1.weight, self.conv1.bias, oc[0].bias), 'flowhead', fold)
+            ops.tc_linear([d.z, net], ops.tc_weights(w_eff), b_eff, in_stats=d.stats, in_gamma=d.gamma, in_beta=d.beta,
+                          in_count=d.count, in_act=ops.ACT_LRELU, in_slope=0.1, epilogue=ops.TC_FLOW, out=delta, cout=64,
+                          w3=_w(oc[2].weight), b3=_w(oc[2].bias), coords1=coords1, coords2=coords2, coords2_out=coords2_out,
+                          flow_out=flow_out)
+            return delta
         a = _lib.FlowOutArgs(ops._p(d.z), ops._p(d.stats, torch.float64), ops._p(d.gamma), ops._p(d.beta), ops._p(net),
                              ops._p(_w(self.conv1.weight)), ops._p(_w(self.conv1.bias)), ops._p(_w(oc[0].weight)),
                              ops._p(_w(oc[0].bias)), ops._p(_w(oc[2].weight)), ops._p(_w(oc[2].bias)), ops._p(coords1),
