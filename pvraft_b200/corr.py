@@ -146,9 +146,10 @@ class CorrBlock(nn.Module):
         ops.corr_feature(a)
         return corr, keep
 
-    def feature_motion_tc(self, coords, flow, motion_encoder):
+    def feature_motion_tc(self, coords, flow, motion_encoder, need_corr=True):
         """Lookup + feature head + MotionEncoder with every 1x1 convolution on the tcgen05 tensor cores
-        (model/corr.py:42-45 and model/update.py:15-21): coords, flow [B,N,3] -> (corr [B,N,64], motion [B,N,64]).
+        (model/corr.py:42-45 and model/update.py:15-21): coords, flow [B,N,3] -> (corr [B,N,64], motion [B,N,64]);
+        with need_corr=False the correlation feature itself is not materialised (one launch fewer) and None is returned.
         Needs ops.tc_supported(N)."""
         b, n, _ = coords.shape
         dev = coords.device
@@ -170,12 +171,26 @@ class CorrBlock(nn.Module):
         a.w_cf, a.b_cf = ops._p(_w(me.conv_flow.weight)), ops._p(_w(me.conv_flow.bias))
         a.B, a.N = b, n
         ops.knn_branch(a)
-        # corr = out_conv[3](PReLU(GN(y1))) + knn_out(kfeat): one GEMM over K = 128 + 64
-        bias = ops.derived((oc[3].bias, self.knn_out.bias), 'sum', lambda x, y: (x.detach() + y.detach()).contiguous())
-        corr = ops.tc_linear([y1, kfeat], ops.tc_weights((oc[3].weight, self.knn_out.weight), kcat=True), bias,
-                             in_stats=stats[0], in_gamma=_w(oc[1].weight), in_beta=_w(oc[1].bias), in_count=float(n) * 16.0,
-                             in_act=ACT_LRELU, in_slope=ops.derived((oc[2].weight,), 'slope', lambda w: float(w.detach().reshape(-1)[0])))
-        cc = ops.tc_linear([corr], ops.tc_weights(me.conv_corr.weight), _w(me.conv_corr.bias), out_act=ACT_RELU)
+        gn = dict(in_stats=stats[0], in_gamma=_w(oc[1].weight), in_beta=_w(oc[1].bias), in_count=float(n) * 16.0, in_act=ACT_LRELU,
+                  in_slope=ops.derived((oc[2].weight,), 'slope', lambda w: float(w.detach().reshape(-1)[0])))
+        if need_corr:
+            # corr = out_conv[3](PReLU(GN(y1))) + knn_out(kfeat): one GEMM over K = 128 + 64
+            bias = ops.derived((oc[3].bias, self.knn_out.bias), 'sum', lambda x, y: (x.detach() + y.detach()).contiguous())
+            corr = ops.tc_linear([y1, kfeat], ops.tc_weights((oc[3].weight, self.knn_out.weight), kcat=True), bias, **gn)
+            cc = ops.tc_linear([corr], ops.tc_weights(me.conv_corr.weight), _w(me.conv_corr.bias), out_act=ACT_RELU)
+        else:
+            # the loop only consumes relu(conv_corr(corr)) (update.py:16), and corr is linear in [a1, kfeat]: fold conv_corr
+            # into the weights, W_cc [W_out | W_kout] with bias W_cc (b_out + b_kout) + b_cc (float64 products, rounded once)
+            def fold(w_cc, b_cc, w_out, b_out, w_kout, b_kout):
+                wc = w_cc.detach().reshape(64, 64).double()
+                wcat = torch.cat([w_out.detach().reshape(64, 128), w_kout.detach().reshape(64, 64)], 1).double()
+                return ((wc @ wcat).float().contiguous(),
+                        (wc @ (b_out.detach().double() + b_kout.detach().double()) + b_cc.detach().double()).float().contiguous())
+
+            w_eff, b_eff = ops.derived((me.conv_corr.weight, me.conv_corr.bias, oc[3].weight, oc[3].bias, self.knn_out.weight,
+                                        self.knn_out.bias), 'corr_cc', fold)
+            corr = None
+            cc = ops.tc_linear([y1, kfeat], ops.tc_weights(w_eff), b_eff, out_act=ACT_RELU, **gn)
         motion = ops.tc_linear([cc, cflow], ops.tc_weights(me.conv.weight), _w(me.conv.bias), out_act=ACT_RELU, tail=flow)
         return corr, motion
 

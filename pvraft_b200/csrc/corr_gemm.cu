@@ -6,24 +6,19 @@
 // The operands are point-major [B,N,C] (K-major for the MMA).  To keep fp32 parity on a TF32 datapath every
 // operand is split once into hi = tf32(x) and lo = tf32(x - hi) (k_tf32_split) and each product is evaluated as
 // hi*hi + lo*hi + hi*lo (the classic 3xTF32 scheme, error ~2^-21 relative per product; the dropped lo*lo term is
-// ~2^-22).  One CTA computes a 128 x 128 tile:
-//   warp 0     TMA producer: cp.async.bulk.tensor.2d loads of the four 128 x 32 operand boxes of a k-block
-//              (SWIZZLE_128B, 16 KB each) into a 2-stage ring, completion on an mbarrier (expect_tx)
-//   warp 1     MMA issuer: one lane issues 3 x 4 tcgen05.mma.kind::tf32 (M=128, N=128, K=8) per k-block into a
-//              128-column TMEM accumulator; tcgen05.commit releases the stage / signals the epilogue
-//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp step) -> divide by sqrt(C) -> global stores
-//              (thread = output row)
+// ~2^-22).  The kernel is persistent (one CTA per SM walks 128 x 128 output tiles); roles and pipeline are described at
+// k_corr_gemm below.  The division by sqrt(C) is a true division, as on the reference's CPU path.
 #include <cuda.h>
 
 #include "common.cuh"
 
 namespace pvraft {
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // TMA producer | MMA issuer | 8 epilogue warps
 constexpr int kTileM = 128, kTileN = 128, kBlockK = 32;     // 32 tf32 = one 128-byte swizzle row
 constexpr int kOperandBytes = kTileM * kBlockK * 4;         // 16 KB
 constexpr int kStageBytes = 4 * kOperandBytes;              // A_hi, A_lo, B_hi, B_lo
-constexpr int kStages = 2;
+constexpr int kStages = 3;
 
 __device__ __forceinline__ unsigned su32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -82,21 +77,60 @@ struct GemmParams {
     float* corr;   // [B,N,N]
     int N, C;
     float scale;   // sqrt(C): the divisor of model/corr.py:99
+    float rscale;  // RN(1 / scale)
+    int tiles_n;   // N / 128
+    long long n_tiles;   // B * tiles_n * tiles_n
 };
 
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive_(void* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(su32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// x / s, correctly rounded, from r = RN(1/s) (Markstein): q0 = x r; q = q0 + (x - q0 s) r.  Three instructions instead of
+// the ~10 of the generic division, bit-identical to it (checked against true division on 1.3e8 values).
+__device__ __forceinline__ float div_by_const(float x, float s, float r) {
+    const float q0 = x * r;
+    return fmaf(fmaf(-q0, s, x), r, q0);
+}
+
+constexpr int kEpiWarps = 8;
+constexpr int kStageCols = 16;                                   // columns staged per epilogue step
+constexpr int kStagePitch = kStageCols + 4;                      // floats; keeps float4 alignment, spreads banks
+constexpr int kEpiStageBytes = kEpiWarps * 32 * kStagePitch * 4; // 20 KB
+
+// Persistent kernel, one CTA per SM, tiles t = blockIdx.x + i * gridDim.x with the column tile fastest (neighbouring CTAs
+// share the A row-panel in L2):
+//   warp 0      TMA producer: four 128 x 32 boxes (A hi/lo, B hi/lo) per k-block into a 3-stage ring
+//   warp 1      MMA issuer (whole warp walks the loop, one elected lane issues): 3 x 4 tcgen05.mma per k-block into one of
+//               two 128-column TMEM accumulators
+//   warps 2-9   epilogue, two warps per TMEM lane quadrant: tcgen05.ld 16 columns -> exact division by sqrt(C) -> transpose
+//               through shared memory -> 64-byte row segments to global.  It drains accumulator t while the MMAs of tile
+//               t+1 run.
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_corr_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const GemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // 1024-byte alignment is required by SWIZZLE_128B; the dynamic segment may start lower, so align by hand
-    // 1024-byte alignment by pointer arithmetic on the shared array: an integer round trip would lose the address space
-    // and turn every shared-memory access below into a generic LD/ST
+    // 1024-byte alignment (SWIZZLE_128B) by pointer arithmetic on the shared array: an integer round trip would lose the
+    // address space and turn every shared-memory access into a generic LD/ST
     unsigned char* tiles = smem_raw + ((1024u - ((unsigned)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
-    __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages], s_tmem_full;
+    float* s_stage = reinterpret_cast<float*>(tiles + (size_t)kStages * kStageBytes);
+    __shared__ __align__(8) unsigned long long s_full[kStages], s_empty[kStages], s_acc_full[2], s_acc_empty[2];
     __shared__ unsigned s_tmem_base;
     const int warp = warp_id(), lane = lane_id();
-    const int tile_n = blockIdx.x, tile_m = blockIdx.y, b = blockIdx.z;
     const int num_kb = p.C / kBlockK;
+    const long long my_tiles = blockIdx.x < p.n_tiles ? (p.n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
@@ -106,93 +140,117 @@ k_corr_gemm(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init_(&s_full[s], 1); mbar_init_(&s_empty[s], 1); }
-        mbar_init_(&s_tmem_full, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init_(&s_acc_full[a], 1); mbar_init_(&s_acc_empty[a], kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {   // 128 fp32 accumulator columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(su32(&s_tmem_base)), "r"(128u) : "memory");
+    if (warp == 2) {   // two 128-column fp32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(su32(&s_tmem_base)), "r"(256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem = s_tmem_base;
+    const int tiles_per_batch = p.tiles_n * p.tiles_n;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            const int row_a = b * p.N + tile_m * kTileM, row_b = b * p.N + tile_n * kTileN;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                const unsigned phase = (unsigned)(kb / kStages) & 1u;
-                mbar_wait_(&s_empty[s], phase ^ 1u);
-                unsigned char* st = tiles + (size_t)s * kStageBytes;
-                mbar_expect_tx_(&s_full[s], kStageBytes);
-                tma_load_2d(st + 0 * kOperandBytes, &map_a_hi, &s_full[s], kb * kBlockK, row_a);
-                tma_load_2d(st + 1 * kOperandBytes, &map_a_lo, &s_full[s], kb * kBlockK, row_a);
-                tma_load_2d(st + 2 * kOperandBytes, &map_b_hi, &s_full[s], kb * kBlockK, row_b);
-                tma_load_2d(st + 3 * kOperandBytes, &map_b_lo, &s_full[s], kb * kBlockK, row_b);
+            int s = 0;
+            unsigned phase = 0;
+            for (long long i = 0; i < my_tiles; ++i) {
+                const long long t = blockIdx.x + i * gridDim.x;
+                const int b = (int)(t / tiles_per_batch), r = (int)(t - (long long)b * tiles_per_batch);
+                const int tile_m = r / p.tiles_n, tile_n = r - tile_m * p.tiles_n;
+                const int row_a = b * p.N + tile_m * kTileM, row_b = b * p.N + tile_n * kTileN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_(&s_empty[s], phase ^ 1u);
+                    unsigned char* st = tiles + (size_t)s * kStageBytes;
+                    mbar_expect_tx_(&s_full[s], kStageBytes);
+                    tma_load_2d(st + 0 * kOperandBytes, &map_a_hi, &s_full[s], kb * kBlockK, row_a);
+                    tma_load_2d(st + 1 * kOperandBytes, &map_a_lo, &s_full[s], kb * kBlockK, row_a);
+                    tma_load_2d(st + 2 * kOperandBytes, &map_b_hi, &s_full[s], kb * kBlockK, row_b);
+                    tma_load_2d(st + 3 * kOperandBytes, &map_b_lo, &s_full[s], kb * kBlockK, row_b);
+                    if (++s == kStages) { s = 0; phase ^= 1u; }
+                }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (a single thread issues on behalf of the CTA) =====
-        if (lane == 0) {
-            constexpr unsigned idesc = umma_idesc_tf32(kTileM, kTileN);
+        // ===== MMA issuer =====
+        constexpr unsigned idesc = umma_idesc_tf32(kTileM, kTileN);
+        int s = 0;
+        unsigned phase = 0;
+        for (long long i = 0; i < my_tiles; ++i) {
+            const int acc = (int)(i & 1);
+            mbar_wait_(&s_acc_empty[acc], (((unsigned)(i >> 1)) & 1u) ^ 1u);   // the epilogue has drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const unsigned tacc = tmem + (unsigned)(acc * kTileN);
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                const unsigned phase = (unsigned)(kb / kStages) & 1u;
                 mbar_wait_(&s_full[s], phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 unsigned char* st = tiles + (size_t)s * kStageBytes;
                 const unsigned long long a_hi = umma_desc(st + 0 * kOperandBytes), a_lo = umma_desc(st + 1 * kOperandBytes);
                 const unsigned long long b_hi = umma_desc(st + 2 * kOperandBytes), b_lo = umma_desc(st + 3 * kOperandBytes);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < kBlockK / 8; ++k) {
-                    // one MMA covers K = 8 tf32 = 32 bytes: advance the start address field by 32 B >> 4 = 2
-                    const unsigned long long off = (unsigned long long)(k * 2);
-                    umma_tf32(tmem, a_hi + off, b_hi + off, idesc, (kb | k) != 0 ? 1u : 0u);
-                    umma_tf32(tmem, a_lo + off, b_hi + off, idesc, 1u);
-                    umma_tf32(tmem, a_hi + off, b_lo + off, idesc, 1u);
+                    for (int k = 0; k < kBlockK / 8; ++k) {
+                        // one MMA covers K = 8 tf32 = 32 bytes: advance the start address field by 32 B >> 4 = 2
+                        const unsigned long long off = (unsigned long long)(k * 2);
+                        umma_tf32(tacc, a_hi + off, b_hi + off, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_tf32(tacc, a_lo + off, b_hi + off, idesc, 1u);
+                        umma_tf32(tacc, a_hi + off, b_lo + off, idesc, 1u);
+                    }
+                    umma_commit(&s_empty[s]);                            // the stage may be refilled once these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(&s_acc_full[acc]);  // accumulator complete
                 }
-                umma_commit(&s_empty[s]);                        // the stage may be refilled once these MMAs retire
-                if (kb == num_kb - 1) umma_commit(&s_tmem_full);  // accumulator complete
+                __syncwarp();
+                if (++s == kStages) { s = 0; phase ^= 1u; }
             }
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> global =====
-        mbar_wait_(&s_tmem_full, 0u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int quad = warp & 3;                      // a warp may only touch TMEM lanes 32*(warp%4) .. +31
-        const int row = quad * 32 + lane;               // accumulator row = TMEM lane
-        float* out = p.corr + ((size_t)b * p.N + (size_t)tile_m * kTileM + row) * p.N + (size_t)tile_n * kTileN;
+        // ===== epilogue: TMEM -> registers -> shared (transpose) -> global =====
+        const int quad = warp & 3;                 // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        const int half = (warp - 2) >> 2;          // columns [64*half, 64*half + 64) of the tile
+        float* stg = s_stage + (size_t)(warp - 2) * 32 * kStagePitch;
+        const int rsub = lane >> 2, cq = lane & 3; // store phase: 8 rows x 4 float4 per instruction
+        for (long long i = 0; i < my_tiles; ++i) {
+            const long long t = blockIdx.x + i * gridDim.x;
+            const int b = (int)(t / tiles_per_batch), r = (int)(t - (long long)b * tiles_per_batch);
+            const int tile_m = r / p.tiles_n, tile_n = r - tile_m * p.tiles_n;
+            const int acc = (int)(i & 1);
+            mbar_wait_(&s_acc_full[acc], ((unsigned)(i >> 1)) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const unsigned tl = tmem + (unsigned)(acc * kTileN) + ((unsigned)(quad * 32) << 16);
+            float* obase = p.corr + ((size_t)b * p.N + (size_t)tile_m * kTileM + quad * 32 + rsub) * p.N + (size_t)tile_n * kTileN + cq * 4;
 #pragma unroll 1
-        for (int c0 = 0; c0 < kTileN; c0 += 32) {
-            unsigned v[32];
-            const unsigned taddr = tmem + ((unsigned)(quad * 32) << 16) + (unsigned)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
-                "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                  "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                  "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int c0 = half * 64; c0 < half * 64 + 64; c0 += kStageCols) {
+                unsigned v[16];
+                tmem_ld16(tl + (unsigned)c0, v);
+                __syncwarp();   // the previous step's readers are done with the staging tile
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float4 o;
-                // corr / sqrt(C) as a true division (model/corr.py:99)
-                o.x = __fdiv_rn(__uint_as_float(v[q * 4 + 0]), p.scale); o.y = __fdiv_rn(__uint_as_float(v[q * 4 + 1]), p.scale);
-                o.z = __fdiv_rn(__uint_as_float(v[q * 4 + 2]), p.scale); o.w = __fdiv_rn(__uint_as_float(v[q * 4 + 3]), p.scale);
-                *reinterpret_cast<float4*>(out + c0 + q * 4) = o;
+                for (int q = 0; q < 4; ++q) {
+                    // corr / sqrt(C) as a true (correctly rounded) division (model/corr.py:99)
+                    *reinterpret_cast<float4*>(stg + lane * kStagePitch + q * 4) =
+                        make_float4(div_by_const(__uint_as_float(v[q * 4 + 0]), p.scale, p.rscale), div_by_const(__uint_as_float(v[q * 4 + 1]), p.scale, p.rscale),
+                                    div_by_const(__uint_as_float(v[q * 4 + 2]), p.scale, p.rscale), div_by_const(__uint_as_float(v[q * 4 + 3]), p.scale, p.rscale));
+                }
+                __syncwarp();
+                float4 o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = *reinterpret_cast<const float4*>(stg + (j * 8 + rsub) * kStagePitch + cq * 4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(obase + (size_t)(j * 8) * p.N + c0) = o[j];
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_(&s_acc_empty[acc]);
         }
     }
-    __syncwarp();   // the producer / MMA roles run on one lane: re-converge before the CTA-wide (aligned) barrier
+    __syncwarp();   // the producer runs on one lane: re-converge before the CTA-wide (aligned) barrier
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
     }
 }
 
@@ -276,10 +334,15 @@ extern "C" int pvraft_corr_matmul_fwd(const float* fmap1, const float* fmap2, in
     if ((rc = make_map(&ma_hi, a_hi, (long long)B * N, C)) || (rc = make_map(&ma_lo, a_lo, (long long)B * N, C)) ||
         (rc = make_map(&mb_hi, b_hi, (long long)B * N, C)) || (rc = make_map(&mb_lo, b_lo, (long long)B * N, C)))
         return rc;
-    GemmParams p{corr, N, C, sqrtf((float)C)};
-    const size_t smem = (size_t)kStages * kStageBytes + 1024;
+    GemmParams p{};
+    p.corr = corr; p.N = N; p.C = C;
+    p.scale = sqrtf((float)C);
+    p.rscale = (float)(1.0 / (double)p.scale);
+    p.tiles_n = N / kTileN;
+    p.n_tiles = (long long)B * p.tiles_n * p.tiles_n;
+    const size_t smem = (size_t)kStages * kStageBytes + kEpiStageBytes + 1024;
     if ((rc = opt_in_smem(k_corr_gemm, smem))) return rc;
-    dim3 grid(N / kTileN, N / kTileM, B);
+    const int grid = (int)(p.n_tiles < sm_count() ? p.n_tiles : sm_count());
     k_corr_gemm<<<grid, kGemmThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
     return check_launch("corr_gemm");
 }

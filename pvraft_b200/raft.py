@@ -48,7 +48,7 @@ class _RaftBase(nn.Module):
         use_tc = ops.tc_supported(n)
         for _ in range(num_iters):
             if use_tc:
-                _, motion = self.corr_block.feature_motion_tc(coords2, flow, me)          # :42 + update.py:83
+                _, motion = self.corr_block.feature_motion_tc(coords2, flow, me, need_corr=False)          # :42 + update.py:83
             else:
                 motion = torch.empty(b, n, 64, dtype=torch.float32, device=xyz1.device)
 

@@ -280,6 +280,8 @@ def test_modules_teacher_forced_vs_reference(dev, fixture, refine):
                 assert rel_err(corr_pm.transpose(1, 2).cpu(), arr[f'it{it}/corr']) < TOL
                 assert rel_err(mot_pm.transpose(1, 2).cpu(), arr[f'it{it}/motion']) < 2 * TOL   # (its input is the computed corr)
                 assert torch.equal(mot_pm[..., 61:], flow)
+                none, mot_f = m.corr_block.feature_motion_tc(coords, flow.contiguous(), m.update_block.motion_encoder, need_corr=False)
+                assert none is None and rel_err(mot_f.transpose(1, 2).cpu(), arr[f'it{it}/motion']) < 2 * TOL   # conv_corr folded
             net2, delta = m.update_block(net, inp, gcorr, flow, g)                 # UpdateBlock.forward
             assert rel_err(net2.cpu(), arr[f'it{it}/net']) < TOL
             assert rel_err(delta.cpu(), arr[f'it{it}/delta']) < 5e-5
