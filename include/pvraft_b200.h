@@ -340,7 +340,7 @@ PVRAFT_API int pvraft_flow_out_fwd(const pvraft_flowout_args* a, void* stream);
  * with q.x = fma(qz,xz, fma(qy,xy, qx*xx)) and |.|^2 = (x*x+y*y)+z*z.  1 <= k <= 32, N >= k.
  * Ties at the k-th place: lowest candidate id.
  * workspace: pvraft_knn_workspace_bytes(B, N) bytes of device scratch (16-byte aligned) enable the
- * x-sorted sweep (N <= 16384); with workspace == NULL (or larger N) the brute-force kernel runs.  Both
+ * uniform-grid search (N <= 16384); with workspace == NULL (or larger N) the brute-force kernel runs.  Both
  * return the same set.
  * --------------------------------------------------------------------------------------------- */
 PVRAFT_API int64_t pvraft_knn_workspace_bytes(int B, int N);

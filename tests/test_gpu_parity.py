@@ -207,6 +207,30 @@ def test_knn_sweep_equals_brute_force(dev):
             assert torch.equal(a, c), (b, n, s, k, mode)
 
 
+def test_knn_grid_hard_distributions(dev):
+    """The grid search must return the brute-force set on clustered, flat, duplicated and far-from-origin clouds and
+    for queries outside the cloud's bounding box (every pruning decision is a bound, never a heuristic)."""
+    from pvraft_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    n = 4096
+    blobs = torch.cat([torch.randn(n // 4, 3, generator=g) * sd + torch.tensor(c) for sd, c in
+                       ((0.05, [0., 0., 0.]), (0.5, [5., 1., -2.]), (2.0, [-20., 10., 3.]), (0.01, [30., 30., 30.]))])
+    flat = torch.rand(n, 3, generator=g) * torch.tensor([50., 50., 0.]) + torch.tensor([0., 0., 1.5])
+    line = torch.rand(n, 1, generator=g) * torch.tensor([[100., 0., 0.]])
+    dup = torch.rand(n // 8, 3, generator=g).repeat(8, 1) * 4.0
+    far = torch.rand(n, 3, generator=g) * 2.0 + 500.0
+    same = torch.ones(n, 3)
+    for name, cloud in (('blobs', blobs), ('flat', flat), ('line', line), ('dup', dup), ('far', far), ('same', same)):
+        xyz = cloud.unsqueeze(0).contiguous().to(dev)
+        lo, hi = cloud.min(0).values, cloud.max(0).values
+        outside = (lo + (hi - lo) * (torch.rand(256, 3, generator=g) * 3.0 - 1.0)).unsqueeze(0).to(dev)   # up to one extent outside
+        for q in (xyz, outside):
+            for mode in (0, 1):
+                a = ops.knn(xyz, q.contiguous(), 32, mode=mode, use_sweep=True).sort(-1).values
+                c = ops.knn(xyz, q.contiguous(), 32, mode=mode, use_sweep=False).sort(-1).values
+                assert torch.equal(a, c), (name, q.shape[1], mode)
+
+
 def test_knn_point_golden(dev):
     from pvraft_b200 import knn_point
     arr, _ = load_golden('knn_point.npz')
