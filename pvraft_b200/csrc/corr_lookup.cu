@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
     int* s_slots = reinterpret_cast<int*>(wbase + K * 8 + VL + 256);     // [32]  kNN slots
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(wbase + K * 8 + VL + 384);   // [2]
     const bool active_warp = w < p.warps;
+    __shared__ int s_next;   // next unclaimed point of the current segment (warps take points dynamically: per-point cost varies)
     // 1/c in double for c = 0..K: (float)(double(sum) * rcp[c]) is the correctly rounded fp32 quotient sum/c for
     // every integer c <= 2^20 (x/c is never within 2^-34 relative of a rounding boundary), without a division
     double* s_rcp = reinterpret_cast<double*>(smem_raw + tab_bytes + (size_t)p.warps * lookup_warp_bytes(K));
@@ -180,24 +181,25 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
             }
             prefetch_row(p.corr_val + (seg + w) * K, K, lane);
         }
+        __syncthreads();   // previous segment's readers are done (table and point counter)
+        if (threadIdx.x == 0) s_next = 2 * p.warps;   // warp w starts with points w and w + warps
         if (SMEM_TAB) {
-            __syncthreads();   // previous segment's readers are done
             for (int i = threadIdx.x; i < p.N * 3; i += blockDim.x) s_tab[i] = __ldg(tab_g + i);
-            __syncthreads();
         }
+        __syncthreads();
         double mom[14];
 #pragma unroll
         for (int i = 0; i < 14; ++i) mom[i] = 0.0;
 
         if (active_warp) {
-            for (long long pt = seg + w; pt < seg_end; pt += p.warps) {
+            int cur = 0;
+            long long nxt = seg + w + p.warps;   // the second point of this warp is fixed as well; later ones are claimed
+            for (long long pt = seg + w; pt < seg_end; cur ^= 1) {
                 const float cx = __ldg(p.coords + pt * 3 + 0);
                 const float cy = __ldg(p.coords + pt * 3 + 1);
                 const float cz = __ldg(p.coords + pt * 3 + 2);
-                const int cur = (int)(((pt - seg) / p.warps) & 1);
                 const int* s_idx = s_stage + cur * K;
                 {   // the other stage is free (its point is finished): start the next row now, a whole point ahead
-                    const long long nxt = pt + p.warps;
                     if (nxt < seg_end) {
                         if (lane == 0) {
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -415,6 +417,11 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                     mom[11] += f2 * f2; mom[12] += f2 * f3; mom[13] += f3 * f3;
                 }
                 __syncwarp();
+                // claim the point after next (its row is fetched while `nxt` is processed)
+                pt = nxt;
+                int claim = 0;
+                if (lane == 0) claim = atomicAdd(&s_next, 1);
+                nxt = seg + __shfl_sync(kFull, claim, 0);
             }
             if (p.moments) {
 #pragma unroll 1

@@ -112,6 +112,160 @@ __global__ void __launch_bounds__(kTopkThreads) k_corr_topk(const float* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Variant for M <= 8192, M % 4 == 0 (the model's case).  The row is staged once as order-preserving keys, 16 bytes per
+// thread and step (thread t owns the float4 columns j*256 + t: coalesced global loads, conflict-free 128-bit shared
+// loads); the K-th largest key is found with three radix passes (11 + 11 + 10 bits) of which only the first counts every
+// key; the ordered compaction scans packed per-chunk counts (11-bit fields) across the block.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTopkThreads) k_corr_topk_vec(const float* __restrict__ corr, int M, int K, float* __restrict__ val,
+                                                                int32_t* __restrict__ idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* s_key = reinterpret_cast<uint4*>(smem_raw);   // [8 * 256]
+    __shared__ int s_hist[2048];
+    __shared__ int s_wsum[kTopkThreads / 32];
+    __shared__ unsigned s_scan[kTopkThreads / 32][6];
+    __shared__ unsigned s_prefix;
+    __shared__ int s_need;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const size_t row = blockIdx.x;
+    const float4* src = reinterpret_cast<const float4*>(corr + row * (size_t)M);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c4 = j * kTopkThreads + tid;
+        uint4 kk = make_uint4(0u, 0u, 0u, 0u);   // padding: below every real key, never selected (K <= M)
+        if (c4 * 4 < M) {
+            const float4 v = __ldg(src + c4);
+            kk = make_uint4(f2key(v.x), f2key(v.y), f2key(v.z), f2key(v.w));
+        }
+        s_key[c4] = kk;
+    }
+    // ---- radix select (each thread only ever reads the keys it wrote) ----
+    // select(sample, floor, need): the need-th largest key among the sample keys (one per thread) or among all keys >= floor.
+    auto select = [&](bool sample, unsigned floor_key, int need, int& need_out) -> unsigned {
+        unsigned prefix = 0u;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+            const int bits = pass < 2 ? 11 : 10;
+            const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+            const unsigned digit_mask = (1u << bits) - 1u;
+            const unsigned hi_mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + bits));
+            for (int i = tid; i < 2048; i += kTopkThreads) s_hist[i] = 0;
+            __syncthreads();
+            if (sample) {
+                const unsigned kx = s_key[tid].x;
+                if ((kx & hi_mask) == prefix) atomicAdd(&s_hist[(kx >> shift) & digit_mask], 1);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint4 kk = s_key[j * kTopkThreads + tid];
+                    if (kk.x >= floor_key && (kk.x & hi_mask) == prefix) atomicAdd(&s_hist[(kk.x >> shift) & digit_mask], 1);
+                    if (kk.y >= floor_key && (kk.y & hi_mask) == prefix) atomicAdd(&s_hist[(kk.y >> shift) & digit_mask], 1);
+                    if (kk.z >= floor_key && (kk.z & hi_mask) == prefix) atomicAdd(&s_hist[(kk.z >> shift) & digit_mask], 1);
+                    if (kk.w >= floor_key && (kk.w & hi_mask) == prefix) atomicAdd(&s_hist[(kk.w >> shift) & digit_mask], 1);
+                }
+            }
+            __syncthreads();
+            // thread t owns bins 8t .. 8t+7; block-wide suffix sums locate the bin holding the `need`-th largest key
+            int h[8], mine = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { h[q] = s_hist[tid * 8 + q]; mine += h[q]; }
+            int incl = mine;   // inclusive suffix sum over the lanes >= lane of this warp
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int a = __shfl_down_sync(kFull, incl, o);
+                if (lane + o < 32) incl += a;
+            }
+            if (lane == 0) s_wsum[w] = incl;
+            __syncthreads();
+            int above = incl;
+            for (int ww = w + 1; ww < kTopkThreads / 32; ++ww) above += s_wsum[ww];
+            const int higher = above - mine;   // keys in bins owned by higher threads
+            if (higher < need && above >= need) {
+                int acc = higher, bin = 7;
+                for (; bin > 0; --bin) {
+                    if (acc + h[bin] >= need) break;
+                    acc += h[bin];
+                }
+                s_need = need - acc;   // rank of the target inside the chosen bin
+                s_prefix = prefix | ((unsigned)(tid * 8 + bin) << shift);
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            need = s_need;
+        }
+        need_out = need;
+        return prefix;
+    };
+    __syncthreads();
+    const unsigned floor_key = 0u;   // (a sampled floor that skips most atomics was tried: the extra passes cost more than they save)
+    int need = 0;
+    const unsigned prefix = select(false, floor_key, K, need);
+    const unsigned T = prefix;   // exact K-th largest key
+    const int need_eq = need;    // how many keys == T belong to the top-K (lowest columns first)
+    // ---- ordered compaction: chunk j = columns [1024 j, 1024 j + 1024), inside a chunk thread order = column order ----
+    unsigned cnt[6] = {0u, 0u, 0u, 0u, 0u, 0u};   // words 0-2: keys > T per chunk (11-bit fields), words 3-5: keys == T
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint4 kk = s_key[j * kTopkThreads + tid];
+        const unsigned g = (kk.x > T) + (kk.y > T) + (kk.z > T) + (kk.w > T);
+        const unsigned q = (kk.x == T) + (kk.y == T) + (kk.z == T) + (kk.w == T);
+        cnt[j / 3] += g << (11 * (j % 3));
+        cnt[3 + j / 3] += q << (11 * (j % 3));
+    }
+    unsigned inc[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) inc[i] = cnt[i];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const unsigned a = __shfl_up_sync(kFull, inc[i], o);
+            if (lane >= o) inc[i] += a;
+        }
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s_scan[w][i] = inc[i];
+    }
+    __syncthreads();
+    unsigned tot[6] = {0u, 0u, 0u, 0u, 0u, 0u}, before[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) before[i] = inc[i] - cnt[i];   // exclusive within the warp
+    for (int ww = 0; ww < kTopkThreads / 32; ++ww) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const unsigned a = s_scan[ww][i];
+            tot[i] += a;
+            if (ww < w) before[i] += a;
+        }
+    }
+    int base_gt = 0, base_eq = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int sh = 11 * (j % 3);
+        int gt_before = base_gt + (int)((before[j / 3] >> sh) & 0x7FFu);
+        int eq_before = base_eq + (int)((before[3 + j / 3] >> sh) & 0x7FFu);
+        base_gt += (int)((tot[j / 3] >> sh) & 0x7FFu);
+        base_eq += (int)((tot[3 + j / 3] >> sh) & 0x7FFu);
+        const int col = (j * kTopkThreads + tid) * 4;
+        const uint4 kk = s_key[j * kTopkThreads + tid];
+        const unsigned ke[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const unsigned key = ke[e];
+            const bool gt = key > T, eq = key == T;
+            if (gt || (eq && eq_before < need_eq)) {
+                const size_t pos = row * (size_t)K + (size_t)(gt_before + min(eq_before, need_eq));
+                val[pos] = key2f(key);
+                idx[pos] = col + e;
+            }
+            gt_before += gt ? 1 : 0;
+            eq_before += eq ? 1 : 0;
+        }
+    }
+}
+
 }  // namespace pvraft
 
 using namespace pvraft;
@@ -121,11 +275,15 @@ extern "C" int pvraft_corr_topk_fwd(const float* corr, int B, int N, int M, int 
     if (B <= 0 || N <= 0 || M <= 0) return fail(PVRAFT_ERR_BAD_ARG, "corr_topk: bad shape");
     if (K < 1 || K > M || K > 1024) return fail(PVRAFT_ERR_UNSUPPORTED, "corr_topk: K=%d with M=%d (need 1 <= K <= min(M,1024))", K, M);
     if (M > 49152) return fail(PVRAFT_ERR_UNSUPPORTED, "corr_topk: M=%d columns (max 49152)", M);
+    const long long rows = (long long)B * N;
+    if (rows > 0x7fffffffLL) return fail(PVRAFT_ERR_UNSUPPORTED, "corr_topk: too many rows");
+    if (M <= 8192 && M % 4 == 0) {
+        k_corr_topk_vec<<<(unsigned)rows, kTopkThreads, 8 * kTopkThreads * sizeof(uint4), (cudaStream_t)stream>>>(corr, M, K, val, idx);
+        return check_launch("corr_topk");
+    }
     const size_t smem = (size_t)(M + (M >> 5) + 4) * 4;
     int rc;
     if ((rc = opt_in_smem(k_corr_topk, smem))) return rc;
-    const long long rows = (long long)B * N;
-    if (rows > 0x7fffffffLL) return fail(PVRAFT_ERR_UNSUPPORTED, "corr_topk: too many rows");
     k_corr_topk<<<(unsigned)rows, kTopkThreads, smem, (cudaStream_t)stream>>>(corr, M, K, val, idx);
     return check_launch("corr_topk");
 }

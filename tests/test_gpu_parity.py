@@ -156,7 +156,8 @@ def test_lookup_full_size_properties(dev):
 # ----------------------------------------------------------------------------------------------------
 # truncation (top-K) and kNN graph
 # ----------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('b,n,m,k', [(2, 64, 256, 64), (1, 128, 1024, 512), (1, 33, 700, 100), (1, 16, 8192, 512)])
+@pytest.mark.parametrize('b,n,m,k', [(2, 64, 256, 64), (1, 128, 1024, 512), (1, 33, 700, 100), (1, 16, 8192, 512),
+                                     (1, 8, 8192, 1024), (1, 8, 8190, 512), (1, 4, 12000, 300), (1, 5, 64, 1), (1, 5, 64, 64)])
 def test_corr_topk(dev, b, n, m, k):
     from pvraft_b200 import ops
     g = torch.Generator().manual_seed(m + k)
@@ -169,6 +170,19 @@ def test_corr_topk(dev, b, n, m, k):
     assert (idx.cpu()[..., 1:] > idx.cpu()[..., :-1]).all()                      # ascending columns
     s = idx.cpu().long().sort(-1).values
     assert (s[..., 1:] > s[..., :-1]).all(), 'duplicate columns'
+
+
+def test_corr_topk_degenerate_rows(dev):
+    """Constant rows (every key ties) and two-valued rows: the lowest columns win the ties."""
+    from pvraft_b200 import ops
+    m, k = 4096, 512
+    corr = torch.zeros(1, 3, m)
+    corr[0, 1] = 2.5
+    corr[0, 2, 1::2] = -1.0                       # 2048 zeros at the even columns, -1 at the odd ones
+    val, idx = ops.corr_topk(corr.to(dev), k)
+    assert torch.equal(idx.cpu()[0, 0].long(), torch.arange(k)) and torch.equal(idx.cpu()[0, 1].long(), torch.arange(k))
+    assert torch.equal(idx.cpu()[0, 2].long(), torch.arange(0, 2 * k, 2))
+    assert torch.equal(val.cpu()[0, 1], torch.full((k,), 2.5)) and torch.equal(val.cpu()[0, 2], torch.zeros(k))
 
 
 @pytest.mark.parametrize('b,n', [(2, 256), (1, 1000), (1, 4096)])
