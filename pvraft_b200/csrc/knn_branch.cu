@@ -5,7 +5,8 @@
 //
 // f_e = (corr, dx, dy, dz) of the 32 selected candidates (knn_sel from the lookup kernel).  The GroupNorm statistics of the
 // [B,64,N,32] tensor follow analytically from the per-sample moments of f that the lookup accumulated, so the affine is
-// folded into the 4->64 convolution and the whole branch is one pass: 4 FMA + max + min per (candidate, channel).
+// folded into the 4->64 convolution and the whole branch is one pass: 4 FMA + max + min per (candidate, channel), the FMAs
+// issued as packed fp32x2 instructions (FFMA2) over candidate pairs.
 // PReLU with slope <= 1 is convex, so max_e PReLU(t_e) = max(PReLU(max_e t_e), PReLU(min_e t_e)) exactly; a learned slope
 // above 1 takes the per-candidate path.
 //
@@ -17,6 +18,18 @@ namespace pvraft {
 
 constexpr int kKbThreads = 256;
 constexpr int kKbTile = 64;
+
+// packed fp32x2 FMA (sm_100 FFMA2): two IEEE fma.rn per instruction, results identical to the scalar form
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
 
 template <bool CONVEX>
 __global__ void __launch_bounds__(kKbThreads) k_knn_branch(const pvraft_knn_branch_args a) {
@@ -68,35 +81,56 @@ __global__ void __launch_bounds__(kKbThreads) k_knn_branch(const pvraft_knn_bran
             }
             cur_b = b;
         }
+        // staged per point as four arrays of 32 (corr, dx, dy, dz): a 128-bit load yields one component of 4 candidates,
+        // i.e. two operand pairs for the packed FMA
         for (int i = tid; i < kKbTile * 32; i += kKbThreads) {
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
             if ((i >> 5) < npts) x = __ldg(reinterpret_cast<const float4*>(a.knn_sel) + row0 * 32 + i);
-            *reinterpret_cast<float4*>(s_sel + i * 4) = x;
+            float* dst = s_sel + (i >> 5) * 128 + (i & 31);
+            dst[0] = x.x; dst[32] = x.y; dst[64] = x.z; dst[96] = x.w;
         }
         __syncthreads();
-        float4 wk[4];
+        float wk[4][4], bk[4];   // [input i][channel c]
 #pragma unroll
-        for (int i = 0; i < 4; ++i) wk[i] = *reinterpret_cast<const float4*>(s_w + i * 64 + tx * 4);
-        const float4 bk = *reinterpret_cast<const float4*>(s_b + tx * 4);
+        for (int i = 0; i < 4; ++i) {
+            const float4 t4 = *reinterpret_cast<const float4*>(s_w + i * 64 + tx * 4);
+            wk[i][0] = t4.x; wk[i][1] = t4.y; wk[i][2] = t4.z; wk[i][3] = t4.w;
+        }
+        {
+            const float4 t4 = *reinterpret_cast<const float4*>(s_b + tx * 4);
+            bk[0] = t4.x; bk[1] = t4.y; bk[2] = t4.z; bk[3] = t4.w;
+        }
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             const int pp = ty * 4 + p;
-            const float4* fp = reinterpret_cast<const float4*>(s_sel) + pp * 32;
+            const float* fp = s_sel + pp * 128;
             float hi[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             float lo[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
-#pragma unroll 8
-            for (int e = 0; e < 32; ++e) {
-                const float4 f = fp[e];
-                float t0 = fmaf(wk[3].x, f.w, fmaf(wk[2].x, f.z, fmaf(wk[1].x, f.y, fmaf(wk[0].x, f.x, bk.x))));
-                float t1 = fmaf(wk[3].y, f.w, fmaf(wk[2].y, f.z, fmaf(wk[1].y, f.y, fmaf(wk[0].y, f.x, bk.y))));
-                float t2 = fmaf(wk[3].z, f.w, fmaf(wk[2].z, f.z, fmaf(wk[1].z, f.y, fmaf(wk[0].z, f.x, bk.z))));
-                float t3 = fmaf(wk[3].w, f.w, fmaf(wk[2].w, f.z, fmaf(wk[1].w, f.y, fmaf(wk[0].w, f.x, bk.w))));
-                if (!CONVEX) {
-                    t0 = t0 >= 0.f ? t0 : slope * t0; t1 = t1 >= 0.f ? t1 : slope * t1;
-                    t2 = t2 >= 0.f ? t2 : slope * t2; t3 = t3 >= 0.f ? t3 : slope * t3;
+#pragma unroll 2
+            for (int e = 0; e < 32; e += 4) {
+                const float4 f0 = *reinterpret_cast<const float4*>(fp + e);        // corr of candidates e..e+3
+                const float4 f1 = *reinterpret_cast<const float4*>(fp + 32 + e);   // dx
+                const float4 f2 = *reinterpret_cast<const float4*>(fp + 64 + e);   // dy
+                const float4 f3 = *reinterpret_cast<const float4*>(fp + 96 + e);   // dz
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    // t_e = fma(w3, dz, fma(w2, dy, fma(w1, dx, fma(w0, corr, b)))) for two candidates per instruction
+                    const float2 b2 = make_float2(bk[c], bk[c]);
+                    float2 ta = fma2(make_float2(wk[0][c], wk[0][c]), make_float2(f0.x, f0.y), b2);
+                    float2 tb = fma2(make_float2(wk[0][c], wk[0][c]), make_float2(f0.z, f0.w), b2);
+                    ta = fma2(make_float2(wk[1][c], wk[1][c]), make_float2(f1.x, f1.y), ta);
+                    tb = fma2(make_float2(wk[1][c], wk[1][c]), make_float2(f1.z, f1.w), tb);
+                    ta = fma2(make_float2(wk[2][c], wk[2][c]), make_float2(f2.x, f2.y), ta);
+                    tb = fma2(make_float2(wk[2][c], wk[2][c]), make_float2(f2.z, f2.w), tb);
+                    ta = fma2(make_float2(wk[3][c], wk[3][c]), make_float2(f3.x, f3.y), ta);
+                    tb = fma2(make_float2(wk[3][c], wk[3][c]), make_float2(f3.z, f3.w), tb);
+                    if (!CONVEX) {
+                        ta.x = ta.x >= 0.f ? ta.x : slope * ta.x; ta.y = ta.y >= 0.f ? ta.y : slope * ta.y;
+                        tb.x = tb.x >= 0.f ? tb.x : slope * tb.x; tb.y = tb.y >= 0.f ? tb.y : slope * tb.y;
+                    }
+                    hi[c] = fmaxf(fmaxf(hi[c], fmaxf(ta.x, ta.y)), fmaxf(tb.x, tb.y));
+                    if (CONVEX) lo[c] = fminf(fminf(lo[c], fminf(ta.x, ta.y)), fminf(tb.x, tb.y));
                 }
-                hi[0] = fmaxf(hi[0], t0); hi[1] = fmaxf(hi[1], t1); hi[2] = fmaxf(hi[2], t2); hi[3] = fmaxf(hi[3], t3);
-                if (CONVEX) { lo[0] = fminf(lo[0], t0); lo[1] = fminf(lo[1], t1); lo[2] = fminf(lo[2], t2); lo[3] = fminf(lo[3], t3); }
             }
             if (CONVEX) {
 #pragma unroll

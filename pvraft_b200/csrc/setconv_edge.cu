@@ -106,6 +106,39 @@ __global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge(const float* __re
 // C % 64 == 0 (the flow head's SetConv, 64 channels, runs every RAFT iteration): lane l owns the adjacent channel pairs
 // (2l, 2l+1) + 64q, so a neighbour row is one 8-byte load per lane and pair, and the per-edge scalars (neighbour id, edge
 // vector) are read back as ONE broadcast 16-byte shared-memory load instead of four shuffles.
+// packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2): two IEEE-rounded operations per instruction, bit-identical to
+// the scalar forms
+__device__ __forceinline__ unsigned long long pk(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 upk(unsigned long long v) {
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(v));
+    return d;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 template <int PAIRS>
 __global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge_pairs(const float* __restrict__ fc1p, const int32_t* __restrict__ nbr,
                                                                      const float* __restrict__ edge_feats, const float* __restrict__ w_fc1,
@@ -123,6 +156,9 @@ __global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge_pairs(const float
         wy[q] = make_float2(__ldg(w_fc1 + (size_t)c * ld + cin + 1), __ldg(w_fc1 + (size_t)(c + 1) * ld + cin + 1));
         wz[q] = make_float2(__ldg(w_fc1 + (size_t)c * ld + cin + 2), __ldg(w_fc1 + (size_t)(c + 1) * ld + cin + 2));
     }
+    unsigned long long wx2[PAIRS], wy2[PAIRS], wz2[PAIRS];
+#pragma unroll
+    for (int q = 0; q < PAIRS; ++q) { wx2[q] = pk(wx[q].x, wx[q].y); wy2[q] = pk(wy[q].x, wy[q].y); wz2[q] = pk(wz[q].x, wz[q].y); }
     const long long total = (long long)B * N;
     long long pt_begin, pt_end;
     split_range(total, gridDim.x, blockIdx.x, pt_begin, pt_end);
@@ -142,26 +178,31 @@ __global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge_pairs(const float
             __syncwarp();
             s_edge[w][lane] = make_float4(__int_as_float(__ldg(nbr + pt * 32 + lane) * C), __ldg(ef), __ldg(ef + 1), __ldg(ef + 2));
             __syncwarp();
-            float2 pi[PAIRS], mx[PAIRS], mn[PAIRS], s1[PAIRS], s2[PAIRS];
+            unsigned long long pi[PAIRS], s1[PAIRS], s2[PAIRS];
+            float2 mx[PAIRS], mn[PAIRS];
 #pragma unroll
             for (int q = 0; q < PAIRS; ++q) {
-                pi[q] = __ldg(reinterpret_cast<const float2*>(P + (size_t)i * C + 64 * q));
+                const float2 t = __ldg(reinterpret_cast<const float2*>(P + (size_t)i * C + 64 * q));
+                pi[q] = pk(t.x, t.y);
                 mx[q] = make_float2(-INFINITY, -INFINITY); mn[q] = make_float2(INFINITY, INFINITY);
-                s1[q] = make_float2(0.f, 0.f); s2[q] = make_float2(0.f, 0.f);
+                s1[q] = pk(0.f, 0.f); s2[q] = pk(0.f, 0.f);
             }
 #pragma unroll 8
             for (int e = 0; e < 32; ++e) {
                 const float4 ed = s_edge[w][e];
                 const float* row = P + __float_as_int(ed.x);
+                const unsigned long long ex = pk(ed.y, ed.y), ey = pk(ed.z, ed.z), ez = pk(ed.w, ed.w);
 #pragma unroll
                 for (int q = 0; q < PAIRS; ++q) {
                     const float2 pj = __ldg(reinterpret_cast<const float2*>(row + 64 * q));
-                    const float y0 = (pj.x - pi[q].x) + fmaf(wz[q].x, ed.w, fmaf(wy[q].x, ed.z, wx[q].x * ed.y));
-                    const float y1 = (pj.y - pi[q].y) + fmaf(wz[q].y, ed.w, fmaf(wy[q].y, ed.z, wx[q].y * ed.y));
-                    mx[q].x = fmaxf(mx[q].x, y0); mx[q].y = fmaxf(mx[q].y, y1);
-                    mn[q].x = fminf(mn[q].x, y0); mn[q].y = fminf(mn[q].y, y1);
-                    s1[q].x += y0; s1[q].y += y1;
-                    s2[q].x = fmaf(y0, y0, s2[q].x); s2[q].y = fmaf(y1, y1, s2[q].y);
+                    // y = (P_j - P_i) + fma(w_z, e_z, fma(w_y, e_y, w_x * e_x)), both channels of the pair at once
+                    const unsigned long long t = fma2(wz2[q], ez, fma2(wy2[q], ey, mul2(wx2[q], ex)));
+                    const unsigned long long y2 = add2(sub2(pk(pj.x, pj.y), pi[q]), t);
+                    const float2 y = upk(y2);
+                    mx[q].x = fmaxf(mx[q].x, y.x); mx[q].y = fmaxf(mx[q].y, y.y);
+                    mn[q].x = fminf(mn[q].x, y.x); mn[q].y = fminf(mn[q].y, y.y);
+                    s1[q] = add2(s1[q], y2);
+                    s2[q] = fma2(y2, y2, s2[q]);
                 }
             }
 #pragma unroll
@@ -169,8 +210,9 @@ __global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge_pairs(const float
                 const size_t o = (size_t)pt * C + 2 * lane + 64 * q;
                 *reinterpret_cast<float2*>(ymax + o) = mx[q];
                 *reinterpret_cast<float2*>(ymin + o) = mn[q];
-                dS[q][0] += (double)s1[q].x; dS[q][1] += (double)s1[q].y;
-                dSS[q][0] += (double)s2[q].x; dSS[q][1] += (double)s2[q].y;
+                const float2 a1 = upk(s1[q]), a2 = upk(s2[q]);
+                dS[q][0] += (double)a1.x; dS[q][1] += (double)a1.y;
+                dSS[q][0] += (double)a2.x; dSS[q][1] += (double)a2.y;
             }
         }
         // block reduction of the per-channel partials -> per-group sums -> one atomic per (group, moment)
