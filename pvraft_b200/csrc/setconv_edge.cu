@@ -8,104 +8,14 @@
 // folded GN scale is >= 0 and lrelu(GN(min_e y_e)) otherwise: the kernel emits both the per-channel max
 // and min of the raw y, plus the double-precision (sum, sum^2) of all N*32*C raw values per group.
 //
-// One warp per point; lane l owns channels l, l+32, l+64, l+96 (coalesced 128-byte row segments).
+// One warp per point; lane l owns the adjacent channel pairs (2l, 2l+1) + 64q: a neighbour row is one 8-byte load per lane
+// and pair, and the per-edge scalars (neighbour id, edge vector) are read back as ONE broadcast 16-byte shared-memory load.
 #include "common.cuh"
 
 namespace pvraft {
 
 constexpr int kEdgeThreads = 256;
 
-template <int SLOTS>
-__global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge(const float* __restrict__ fc1p, const int32_t* __restrict__ nbr,
-                                                               const float* __restrict__ edge_feats, const float* __restrict__ w_fc1,
-                                                               int cin, int B, int N, int C, float* __restrict__ ymax,
-                                                               float* __restrict__ ymin, double* __restrict__ stats) {
-    __shared__ double s_part[kEdgeThreads / 32][128][2];
-    const int lane = lane_id(), w = warp_id(), nwarps = kEdgeThreads / 32;
-    const int ld = cin + 3;
-    float wx[SLOTS], wy[SLOTS], wz[SLOTS];
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-        const int c = lane + 32 * s;
-        wx[s] = c < C ? __ldg(w_fc1 + (size_t)c * ld + cin + 0) : 0.f;
-        wy[s] = c < C ? __ldg(w_fc1 + (size_t)c * ld + cin + 1) : 0.f;
-        wz[s] = c < C ? __ldg(w_fc1 + (size_t)c * ld + cin + 2) : 0.f;
-    }
-    const long long total = (long long)B * N;
-    long long pt_begin, pt_end;
-    split_range(total, gridDim.x, blockIdx.x, pt_begin, pt_end);
-    long long seg = pt_begin;
-    while (seg < pt_end) {
-        const int b = (int)(seg / N);
-        long long seg_end = (long long)(b + 1) * N;
-        if (seg_end > pt_end) seg_end = pt_end;
-        double dS[SLOTS], dSS[SLOTS];
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) { dS[s] = 0.0; dSS[s] = 0.0; }
-        const float* P = fc1p + (size_t)b * N * C;
-        for (long long pt = seg + w; pt < seg_end; pt += nwarps) {
-            const int i = (int)(pt - (long long)b * N);
-            const int my_nbr = __ldg(nbr + pt * 32 + lane);
-            // lane e fetches the edge feature of neighbour e (graph.edge_feats = x_j - x_i, gconv.py:66)
-            const float* ef = edge_feats + ((size_t)pt * 32 + lane) * 3;
-            const float rx = __ldg(ef), ry = __ldg(ef + 1), rz = __ldg(ef + 2);
-            float pi[SLOTS], mx[SLOTS], mn[SLOTS], s1[SLOTS], s2[SLOTS];
-#pragma unroll
-            for (int s = 0; s < SLOTS; ++s) {
-                const int c = lane + 32 * s;
-                pi[s] = c < C ? __ldg(P + (size_t)i * C + c) : 0.f;
-                mx[s] = -INFINITY; mn[s] = INFINITY; s1[s] = 0.f; s2[s] = 0.f;
-            }
-#pragma unroll 4
-            for (int e = 0; e < 32; ++e) {
-                const int j = __shfl_sync(kFull, my_nbr, e);
-                const float ex = __shfl_sync(kFull, rx, e), ey = __shfl_sync(kFull, ry, e), ez = __shfl_sync(kFull, rz, e);
-#pragma unroll
-                for (int s = 0; s < SLOTS; ++s) {
-                    const int c = lane + 32 * s;
-                    if (c < C) {
-                        const float pj = __ldg(P + (size_t)j * C + c);
-                        const float y = (pj - pi[s]) + fmaf(wz[s], ez, fmaf(wy[s], ey, wx[s] * ex));
-                        mx[s] = fmaxf(mx[s], y);
-                        mn[s] = fminf(mn[s], y);
-                        s1[s] += y;
-                        s2[s] = fmaf(y, y, s2[s]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < SLOTS; ++s) {
-                const int c = lane + 32 * s;
-                if (c < C) {
-                    ymax[(size_t)pt * C + c] = mx[s];
-                    ymin[(size_t)pt * C + c] = mn[s];
-                    dS[s] += (double)s1[s];
-                    dSS[s] += (double)s2[s];
-                }
-            }
-        }
-        // block reduction of the per-channel partials -> per-group sums -> one atomic per (group, moment)
-        __syncthreads();
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            s_part[w][lane + 32 * s][0] = dS[s];
-            s_part[w][lane + 32 * s][1] = dSS[s];
-        }
-        __syncthreads();
-        if (threadIdx.x < 16) {
-            const int g = threadIdx.x >> 1, m = threadIdx.x & 1, gsz = C / PVRAFT_GN_GROUPS;
-            double acc = 0.0;
-            for (int c = g * gsz; c < (g + 1) * gsz; ++c)
-                for (int ww = 0; ww < nwarps; ++ww) acc += s_part[ww][c][m];
-            if (acc != 0.0) atomicAdd(stats + (size_t)b * 16 + threadIdx.x, acc);
-        }
-        seg = seg_end;
-    }
-}
-
-// C % 64 == 0 (the flow head's SetConv, 64 channels, runs every RAFT iteration): lane l owns the adjacent channel pairs
-// (2l, 2l+1) + 64q, so a neighbour row is one 8-byte load per lane and pair, and the per-edge scalars (neighbour id, edge
-// vector) are read back as ONE broadcast 16-byte shared-memory load instead of four shuffles.
 // packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2): two IEEE-rounded operations per instruction, bit-identical to
 // the scalar forms
 __device__ __forceinline__ unsigned long long pk(float lo, float hi) {
@@ -151,7 +61,7 @@ __global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge_pairs(const float
     float2 wx[PAIRS], wy[PAIRS], wz[PAIRS];
 #pragma unroll
     for (int q = 0; q < PAIRS; ++q) {
-        const int c = 2 * lane + 64 * q;
+        const int c = min(2 * lane + 64 * q, C - 2);   // (lanes past C replicate the last pair; their results are dropped)
         wx[q] = make_float2(__ldg(w_fc1 + (size_t)c * ld + cin + 0), __ldg(w_fc1 + (size_t)(c + 1) * ld + cin + 0));
         wy[q] = make_float2(__ldg(w_fc1 + (size_t)c * ld + cin + 1), __ldg(w_fc1 + (size_t)(c + 1) * ld + cin + 1));
         wz[q] = make_float2(__ldg(w_fc1 + (size_t)c * ld + cin + 2), __ldg(w_fc1 + (size_t)(c + 1) * ld + cin + 2));
@@ -170,7 +80,11 @@ __global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge_pairs(const float
         double dS[PAIRS][2], dSS[PAIRS][2];
 #pragma unroll
         for (int q = 0; q < PAIRS; ++q) { dS[q][0] = dS[q][1] = 0.0; dSS[q][0] = dSS[q][1] = 0.0; }
-        const float* P = fc1p + (size_t)b * N * C + 2 * lane;
+        bool on[PAIRS];   // C need not fill the last group of 64 channels (encoder layers: 16, 48, 96)
+        int coff[PAIRS];
+#pragma unroll
+        for (int q = 0; q < PAIRS; ++q) { on[q] = 2 * lane + 64 * q < C; coff[q] = on[q] ? 2 * lane + 64 * q : 0; }
+        const float* P = fc1p + (size_t)b * N * C;
         for (long long pt = seg + w; pt < seg_end; pt += nwarps) {
             const int i = (int)(pt - (long long)b * N);
             // lane e parks neighbour e: id and edge feature x_j - x_i (graph.edge_feats, gconv.py:66)
@@ -182,7 +96,7 @@ __global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge_pairs(const float
             float2 mx[PAIRS], mn[PAIRS];
 #pragma unroll
             for (int q = 0; q < PAIRS; ++q) {
-                const float2 t = __ldg(reinterpret_cast<const float2*>(P + (size_t)i * C + 64 * q));
+                const float2 t = __ldg(reinterpret_cast<const float2*>(P + (size_t)i * C + coff[q]));
                 pi[q] = pk(t.x, t.y);
                 mx[q] = make_float2(-INFINITY, -INFINITY); mn[q] = make_float2(INFINITY, INFINITY);
                 s1[q] = pk(0.f, 0.f); s2[q] = pk(0.f, 0.f);
@@ -194,7 +108,7 @@ __global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge_pairs(const float
                 const unsigned long long ex = pk(ed.y, ed.y), ey = pk(ed.z, ed.z), ez = pk(ed.w, ed.w);
 #pragma unroll
                 for (int q = 0; q < PAIRS; ++q) {
-                    const float2 pj = __ldg(reinterpret_cast<const float2*>(row + 64 * q));
+                    const float2 pj = __ldg(reinterpret_cast<const float2*>(row + coff[q]));
                     // y = (P_j - P_i) + fma(w_z, e_z, fma(w_y, e_y, w_x * e_x)), both channels of the pair at once
                     const unsigned long long t = fma2(wz2[q], ez, fma2(wy2[q], ey, mul2(wx2[q], ex)));
                     const unsigned long long y2 = add2(sub2(pk(pj.x, pj.y), pi[q]), t);
@@ -207,9 +121,11 @@ __global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge_pairs(const float
             }
 #pragma unroll
             for (int q = 0; q < PAIRS; ++q) {
-                const size_t o = (size_t)pt * C + 2 * lane + 64 * q;
-                *reinterpret_cast<float2*>(ymax + o) = mx[q];
-                *reinterpret_cast<float2*>(ymin + o) = mn[q];
+                const size_t o = (size_t)pt * C + coff[q];
+                if (on[q]) {
+                    *reinterpret_cast<float2*>(ymax + o) = mx[q];
+                    *reinterpret_cast<float2*>(ymin + o) = mn[q];
+                }
                 const float2 a1 = upk(s1[q]), a2 = upk(s2[q]);
                 dS[q][0] += (double)a1.x; dS[q][1] += (double)a1.y;
                 dSS[q][0] += (double)a2.x; dSS[q][1] += (double)a2.y;
@@ -221,8 +137,10 @@ __global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge_pairs(const float
         for (int q = 0; q < PAIRS; ++q) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                s_part[w][2 * lane + 64 * q + h][0] = dS[q][h];
-                s_part[w][2 * lane + 64 * q + h][1] = dSS[q][h];
+                if (on[q]) {
+                    s_part[w][2 * lane + 64 * q + h][0] = dS[q][h];
+                    s_part[w][2 * lane + 64 * q + h][1] = dSS[q][h];
+                }
             }
         }
         __syncthreads();
@@ -252,20 +170,13 @@ extern "C" int pvraft_setconv_edge_fwd(const float* fc1p, const int32_t* nbr, co
     if (g > need) g = need;
     const int grid = (int)(g < 1 ? 1 : g);
     cudaStream_t st = (cudaStream_t)stream;
-    const int slots = (C + 31) / 32;
-    if (C == 64) {
+    if (C <= 64) {
         k_setconv_edge_pairs<1><<<grid, kEdgeThreads, 0, st>>>(fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats);
         return check_launch("setconv_edge");
     }
-    if (C == 128) {
+    if (C <= 128) {
         k_setconv_edge_pairs<2><<<grid, kEdgeThreads, 0, st>>>(fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats);
         return check_launch("setconv_edge");
     }
-    switch (slots) {
-        case 1: k_setconv_edge<1><<<grid, kEdgeThreads, 0, st>>>(fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats); break;
-        case 2: k_setconv_edge<2><<<grid, kEdgeThreads, 0, st>>>(fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats); break;
-        case 3: k_setconv_edge<3><<<grid, kEdgeThreads, 0, st>>>(fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats); break;
-        default: k_setconv_edge<4><<<grid, kEdgeThreads, 0, st>>>(fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats); break;
-    }
-    return check_launch("setconv_edge");
+    return fail(PVRAFT_ERR_UNSUPPORTED, "setconv_edge: C=%d", C);
 }

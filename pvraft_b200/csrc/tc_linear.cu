@@ -127,6 +127,29 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, unsigned (&v)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// thread-per-row values of a [32 rows x 16 columns] block -> shared-memory transpose -> stores of 8 rows x 64 B per instruction
+// (thread-per-row stores would scatter 32 half-filled sectors per instruction).  stg: this warp's [32][20] staging tile.
+constexpr int kTcPitch16 = 20;
+__device__ __forceinline__ void stage_store16(float* __restrict__ stg, int lane, const float (&y)[16], float* __restrict__ gbase, int ld) {
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(stg + lane * kTcPitch16 + q * 4) = make_float4(y[q * 4], y[q * 4 + 1], y[q * 4 + 2], y[q * 4 + 3]);
+    __syncwarp();
+    const int rsub = lane >> 2, cq = lane & 3;
+    float4 o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = *reinterpret_cast<const float4*>(stg + (j * 8 + rsub) * kTcPitch16 + cq * 4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(gbase + (size_t)(j * 8 + rsub) * ld + cq * 4) = o[j];
+}
 __device__ __forceinline__ bool telect_one() {
     unsigned pred;
     asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
@@ -138,7 +161,6 @@ __device__ __forceinline__ float tsigmoid(float x) { return 1.f / (1.f + expf(-x
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, int quad, int half, int lane, int row0, int sample,
                                             const float* __restrict__ s_bias, float* __restrict__ s_stage, float* __restrict__ s_part) {
     const int row = row0 + quad * 32 + lane;
-    const bool live = row < p.M;
     const int gsz = p.cout / PVRAFT_GN_GROUPS;
     const unsigned tl = tacc + ((unsigned)(quad * 32) << 16);
     if (p.epi == TC_EPI_PLAIN) {
@@ -236,26 +258,24 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
         }
     } else if (p.epi == TC_EPI_GRU_ZR) {
         // accumulator columns 0..63 = z pre-activation, 64..127 = r pre-activation (model/update.py:34-35)
-        for (int c0 = half * 32; c0 < 64; c0 += 64) {
-            unsigned vz[32], vr[32];
-            tmem_ld32(tl + (unsigned)c0, vz);
-            tmem_ld32(tl + (unsigned)(64 + c0), vr);
-            if (live) {
+        float* stg = s_stage + (size_t)(half * 4 + quad) * 32 * kTcPitch16;
+        for (int c = half * 32; c < half * 32 + 32; c += 16) {
+            unsigned vz[16], vr[16];
+            tmem_ld16(tl + (unsigned)c, vz);
+            tmem_ld16(tl + (unsigned)(64 + c), vr);
+            float z[16], rh[16];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int c = c0 + q * 4;
-                    const float4 hv = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)row * 64 + c));
-                    const float4 bz = *reinterpret_cast<const float4*>(s_bias + c);
-                    const float4 br = *reinterpret_cast<const float4*>(s_bias + p.N + c);
-                    float4 z, rh;
-                    z.x = tsigmoid(__uint_as_float(vz[q * 4 + 0]) + bz.x); z.y = tsigmoid(__uint_as_float(vz[q * 4 + 1]) + bz.y);
-                    z.z = tsigmoid(__uint_as_float(vz[q * 4 + 2]) + bz.z); z.w = tsigmoid(__uint_as_float(vz[q * 4 + 3]) + bz.w);
-                    rh.x = tsigmoid(__uint_as_float(vr[q * 4 + 0]) + br.x) * hv.x; rh.y = tsigmoid(__uint_as_float(vr[q * 4 + 1]) + br.y) * hv.y;
-                    rh.z = tsigmoid(__uint_as_float(vr[q * 4 + 2]) + br.z) * hv.z; rh.w = tsigmoid(__uint_as_float(vr[q * 4 + 3]) + br.w) * hv.w;
-                    *reinterpret_cast<float4*>(p.out + (size_t)row * 64 + c) = z;
-                    *reinterpret_cast<float4*>(p.out2 + (size_t)row * 64 + c) = rh;
-                }
+            for (int q = 0; q < 4; ++q) {
+                const float4 hv = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)row * 64 + c + q * 4));
+                const float4 bz = *reinterpret_cast<const float4*>(s_bias + c + q * 4);
+                const float4 br = *reinterpret_cast<const float4*>(s_bias + p.N + c + q * 4);
+                z[q * 4 + 0] = tsigmoid(__uint_as_float(vz[q * 4 + 0]) + bz.x); z[q * 4 + 1] = tsigmoid(__uint_as_float(vz[q * 4 + 1]) + bz.y);
+                z[q * 4 + 2] = tsigmoid(__uint_as_float(vz[q * 4 + 2]) + bz.z); z[q * 4 + 3] = tsigmoid(__uint_as_float(vz[q * 4 + 3]) + bz.w);
+                rh[q * 4 + 0] = tsigmoid(__uint_as_float(vr[q * 4 + 0]) + br.x) * hv.x; rh[q * 4 + 1] = tsigmoid(__uint_as_float(vr[q * 4 + 1]) + br.y) * hv.y;
+                rh[q * 4 + 2] = tsigmoid(__uint_as_float(vr[q * 4 + 2]) + br.z) * hv.z; rh[q * 4 + 3] = tsigmoid(__uint_as_float(vr[q * 4 + 3]) + br.w) * hv.w;
             }
+            stage_store16(stg, lane, z, p.out + (size_t)(row0 + quad * 32) * 64 + c, 64);
+            stage_store16(stg, lane, rh, p.out2 + (size_t)(row0 + quad * 32) * 64 + c, 64);
         }
     } else if (p.epi == TC_EPI_FLOW) {
         // y = relu(acc + b) (flow_head.out_conv.0/1); delta = w3 . y + b3 (out_conv.2); RAFT update of the coordinates.
@@ -297,24 +317,22 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
         asm volatile("bar.sync 3, 256;" ::: "memory");   // the exchange buffer is free for the next tile
     } else {
         // q = tanh(acc + b); h' = (1 - z) h + z q   (model/update.py:37-39)
-        for (int c0 = half * 32; c0 < 64; c0 += 64) {
-            unsigned vq[32];
-            tmem_ld32(tl + (unsigned)c0, vq);
-            if (live) {
+        float* stg = s_stage + (size_t)(half * 4 + quad) * 32 * kTcPitch16;
+        for (int c = half * 32; c < half * 32 + 32; c += 16) {
+            unsigned vq[16];
+            tmem_ld16(tl + (unsigned)c, vq);
+            float o[16];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int c = c0 + q * 4;
-                    const float4 hv = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)row * 64 + c));
-                    const float4 zv = __ldg(reinterpret_cast<const float4*>(p.z + (size_t)row * 64 + c));
-                    const float4 bq = *reinterpret_cast<const float4*>(s_bias + c);
-                    float4 o;
-                    o.x = (1.f - zv.x) * hv.x + zv.x * tanhf(__uint_as_float(vq[q * 4 + 0]) + bq.x);
-                    o.y = (1.f - zv.y) * hv.y + zv.y * tanhf(__uint_as_float(vq[q * 4 + 1]) + bq.y);
-                    o.z = (1.f - zv.z) * hv.z + zv.z * tanhf(__uint_as_float(vq[q * 4 + 2]) + bq.z);
-                    o.w = (1.f - zv.w) * hv.w + zv.w * tanhf(__uint_as_float(vq[q * 4 + 3]) + bq.w);
-                    *reinterpret_cast<float4*>(p.out + (size_t)row * 64 + c) = o;
-                }
+            for (int q = 0; q < 4; ++q) {
+                const float4 hv = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)row * 64 + c + q * 4));
+                const float4 zv = __ldg(reinterpret_cast<const float4*>(p.z + (size_t)row * 64 + c + q * 4));
+                const float4 bq = *reinterpret_cast<const float4*>(s_bias + c + q * 4);
+                o[q * 4 + 0] = (1.f - zv.x) * hv.x + zv.x * tanhf(__uint_as_float(vq[q * 4 + 0]) + bq.x);
+                o[q * 4 + 1] = (1.f - zv.y) * hv.y + zv.y * tanhf(__uint_as_float(vq[q * 4 + 1]) + bq.y);
+                o[q * 4 + 2] = (1.f - zv.z) * hv.z + zv.z * tanhf(__uint_as_float(vq[q * 4 + 2]) + bq.z);
+                o[q * 4 + 3] = (1.f - zv.w) * hv.w + zv.w * tanhf(__uint_as_float(vq[q * 4 + 3]) + bq.w);
             }
+            stage_store16(stg, lane, o, p.out + (size_t)(row0 + quad * 32) * 64 + c, 64);
         }
     }
 }
@@ -360,7 +378,7 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
     float* s_scale = reinterpret_cast<float*>(w_res + (p.w_resident ? (size_t)num_kb * 2 * w_bytes : 0));   // [K]
     float* s_bias = s_scale + 4 * p.K;                                            // ([2 groups][scale K | shift K] above)                                                // [2 * N]
     float* s_estage = s_bias + 2 * p.N;                                           // [4 warps][32][36] epilogue staging
-    float* s_part = s_estage + (p.epi == TC_EPI_PLAIN ? 8 * 32 * 36 : 0);           // (the GRU epilogues do not stage)                                       // [4 warps][128 columns][2]
+    float* s_part = s_estage + (p.epi == TC_EPI_PLAIN ? 8 * 32 * 36 : (p.epi == TC_EPI_FLOW ? 0 : 8 * 32 * kTcPitch16));   // staging tiles by epilogue                                       // [4 warps][128 columns][2]
     __shared__ __align__(8) unsigned long long s_full[kTcMaxStages], s_ready[kTcMaxStages], s_empty[kTcMaxStages];
     __shared__ __align__(8) unsigned long long s_acc_full[2], s_acc_empty[2], s_w_full;
     __shared__ unsigned s_tmem_base;
@@ -670,7 +688,7 @@ extern "C" int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream
     if ((rc = tc_make_map(&mmin, a->in_min ? a->in_min : a->in[0], M, a->in_channels[0], a->in_channels[0], kTcM))) return rc;
     const size_t a_stage = (size_t)2 * kTcABytes;
     const size_t w_all = (size_t)(K / kTcKB) * 2 * a->n_pad * kTcKB * 4;          // hi + lo of the whole weight matrix
-    const size_t fixed = (size_t)(4 * K + 2 * a->n_pad + (a->epilogue == TC_EPI_PLAIN ? 8 * 32 * 36 : 0) + 4 * 128 * 2) * sizeof(float) + 1024 + 64;
+    const size_t fixed = (size_t)(4 * K + 2 * a->n_pad + (a->epilogue == TC_EPI_PLAIN ? 8 * 32 * 36 : (a->epilogue == TC_EPI_FLOW ? 0 : 8 * 32 * 20)) + 4 * 128 * 2) * sizeof(float) + 1024 + 64;
     const size_t budget = (size_t)kSmemBudget - 2048 /* static barriers */ - fixed;
     // Weights stay resident in shared memory when that still leaves a ring of >= 3 activation stages (re-streaming the
     // same few KB per tile from every SM hot-spots a handful of L2 slices); otherwise they travel with the k-blocks.

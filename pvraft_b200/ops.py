@@ -39,8 +39,34 @@ def _count(rc, what):
     launch_count += 1
 
 
+_ARENA = None   # [buffer [n,B,8,2] f64, next free block]: zeroed accumulators handed out inside a `stats_arena` scope
+
+
+class stats_arena:
+    """Scope in which `new_stats` (and the lookup's moment accumulator) are slices of ONE zero-filled buffer instead of a
+    memset launch each: the RAFT loop needs 5 blocks per iteration (`with ops.stats_arena(b, dev, 5 * iters)`)."""
+
+    def __init__(self, b, device, blocks):
+        self.buf = [torch.zeros(blocks, b, 8, 2, dtype=torch.float64, device=device), 0]
+
+    def __enter__(self):
+        global _ARENA
+        self.prev, _ARENA = _ARENA, self.buf
+        return self
+
+    def __exit__(self, *exc):
+        global _ARENA
+        _ARENA = self.prev
+        return False
+
+
 def new_stats(b, device, n=1):
     """Zeroed GroupNorm accumulators: n x [B,8,2] doubles (one cudaMemset for all of them)."""
+    if _ARENA is not None:
+        buf, pos = _ARENA
+        if pos + n <= buf.shape[0] and buf.shape[1] == b and buf.device == torch.device(device):
+            _ARENA[1] = pos + n
+            return buf[pos:pos + n]
     return torch.zeros(n, b, 8, 2, dtype=torch.float64, device=device)
 
 
@@ -84,7 +110,7 @@ def corr_lookup(corr_val, corr_idx, xyz2, coords, levels, base_scale, vox=None, 
     if knn_sel is None:
         knn_sel = torch.empty(b, n, KNN, 4, dtype=torch.float32, device=dev)
     if moments is None:
-        moments = torch.zeros(b, MOMENTS, dtype=torch.float64, device=dev)
+        moments = new_stats(b, dev, 1).view(b, MOMENTS) if MOMENTS == 16 else torch.zeros(b, MOMENTS, dtype=torch.float64, device=dev)
     slots = torch.empty(b, n, KNN, dtype=torch.int32, device=dev) if want_slots else None
     cube = torch.empty(b, n, k, levels, dtype=torch.int8, device=dev) if want_cube else None
     _count(lib().pvraft_corr_lookup_fwd(_p(corr_val), _p(corr_idx, torch.int32), _p(xyz2), _p(coords), b, n, k, levels,

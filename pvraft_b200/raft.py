@@ -46,6 +46,11 @@ class _RaftBase(nn.Module):
         preds = []
         me = self.update_block.motion_encoder
         use_tc = ops.tc_supported(n)
+        with ops.stats_arena(b, xyz1.device, 5 * num_iters):   # moments + 4 GroupNorm accumulators per iteration, one memset
+            return self._iterate_body(xyz1, graph_context, net, inp, num_iters, keep_all, coords2, flow, preds, me, use_tc)
+
+    def _iterate_body(self, xyz1, graph_context, net, inp, num_iters, keep_all, coords2, flow, preds, me, use_tc):
+        b, n, _ = xyz1.shape
         for _ in range(num_iters):
             if use_tc:
                 _, motion = self.corr_block.feature_motion_tc(coords2, flow, me, need_corr=False)          # :42 + update.py:83
