@@ -13,6 +13,8 @@
 // Distances reproduce the reference's expanded form bit-for-bit on the CPU oracle: |q|^2 and |x|^2 as
 // (x*x+y*y)+z*z, q.x as fma(z,z',fma(y,y',x*x')); ranking is on (distance, original id), so the result does not
 // depend on the visiting order.  Clouds too large for the shared-memory sort fall back to the brute-force kernel.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pvraft {
@@ -34,23 +36,27 @@ __device__ __forceinline__ float ref_distance(int mode, float qx, float qy, floa
     return __fadd_rn(__fadd_rn(__fmul_rn(-2.f, dot), qn), p.w);                  // pointconv.py:21-24
 }
 
-// insert the candidates flagged in `cand` (one per lane: d, id) into the warp-resident best set
-__device__ __forceinline__ void insert_candidates(unsigned cand, float d, int id, float& bd, int& bi, float& tau, int& tau_i) {
+// The warp keeps its current k best SORTED across the lanes (lane i = i-th best, lanes >= k hold +inf sentinels), so an
+// insertion is one ballot + one shuffle-up instead of a full warp reduction for the new k-th distance.
+// insert the candidates flagged in `cand` (one per lane: d, id); tau / tau_i = the current k-th (distance, id)
+__device__ __forceinline__ void insert_candidates(unsigned cand, float d, int id, float& bd, int& bi, float& tau, int& tau_i, int k) {
+    const int lane = lane_id();
     while (cand) {
         const int src = __ffs(cand) - 1;
         cand &= cand - 1;
         const float cd = __shfl_sync(kFull, d, src);
         const int cid = __shfl_sync(kFull, id, src);
         if (worse(cd, cid, tau, tau_i)) continue;   // tau may have tightened since the ballot
-        if (bd == tau && bi == tau_i) { bd = cd; bi = cid; }   // replace the current worst (pairs are distinct)
-        float md = bd; int mi = bi;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float od = __shfl_xor_sync(kFull, md, o);
-            const int oi = __shfl_xor_sync(kFull, mi, o);
-            if (worse(od, oi, md, mi)) { md = od; mi = oi; }
+        const unsigned behind = __ballot_sync(kFull, worse(bd, bi, cd, cid));   // a suffix of the lanes: they move up by one
+        const float nd = __shfl_up_sync(kFull, bd, 1);
+        const int ni = __shfl_up_sync(kFull, bi, 1);
+        if ((behind >> lane) & 1u) {
+            const bool first = lane == 0 || !((behind >> (lane - 1)) & 1u);
+            bd = first ? cd : nd;
+            bi = first ? cid : ni;
         }
-        tau = md; tau_i = mi;
+        tau = __shfl_sync(kFull, bd, k - 1);
+        tau_i = __shfl_sync(kFull, bi, k - 1);
     }
 }
 
@@ -84,10 +90,10 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn(const float* __restrict__ x
         qx = __ldg(Q); qy = __ldg(Q + 1); qz = __ldg(Q + 2);
     }
     const float qn = sqnorm(qx, qy, qz);
-    float bd = lane < k ? INFINITY : -INFINITY;
-    int bi = lane < k ? 0x7fffffff - lane : -1;   // distinct sentinels: exactly one lane is "the worst"
+    float bd = INFINITY;                 // sorted list of (distance, id): +inf sentinels with ascending ids
+    int bi = 0x7fffff00 + lane;
     float tau = INFINITY;
-    int tau_i = 0x7fffffff;
+    int tau_i = 0x7fffff00 + k - 1;
     for (int base = 0; base < N; base += kKnnTile) {
         const int cnt = min(kKnnTile, N - base);
         __syncthreads();
@@ -103,7 +109,7 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn(const float* __restrict__ x
             const int id = base + i;
             if (i < cnt) d = ref_distance(mode, qx, qy, qz, qn, s_pts[i]);
             const unsigned cand = __ballot_sync(kFull, i < cnt && !worse(d, id, tau, tau_i));
-            insert_candidates(cand, d, id, bd, bi, tau, tau_i);
+            insert_candidates(cand, d, id, bd, bi, tau, tau_i, k);
         }
     }
     if (live) write_result(X, qx, qy, qz, lane, k, bi, (size_t)b * S + q, out, rel);
@@ -117,7 +123,7 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn(const float* __restrict__ x
 // points in cells < c.  A run of cells along x is therefore one contiguous range of the sorted array.
 constexpr int kMaxCells = 32768;
 constexpr int kMaxGridDim = 64;
-constexpr float kCellOcc = 3.0f;
+constexpr float kCellOcc = 3.0f;   // (the time is flat between 1.5 and 16 points per cell: insertions dominate, not the scan)
 
 struct GridParams {      // one per sample, written by k_grid_sort
     float gmin[3], h[3], inv_h[3];
@@ -131,7 +137,7 @@ __device__ __forceinline__ int cell_coord(float v, float gmin, float inv_h, int 
     return c < 0 ? 0 : (c >= G ? G - 1 : c);
 }
 
-__global__ void __launch_bounds__(1024) k_grid_sort(const float* __restrict__ xyz, int N, int NP /*pow2 >= N*/, GridParams* __restrict__ params,
+__global__ void __launch_bounds__(1024) k_grid_sort(const float* __restrict__ xyz, int N, int NP /*pow2 >= N*/, float occ, GridParams* __restrict__ params,
                                                      float4* __restrict__ sorted, int32_t* __restrict__ ids, unsigned* __restrict__ keys) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* s = reinterpret_cast<unsigned long long*>(smem_raw);   // (cell id << 32) | point id
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(1024) k_grid_sort(const float* __restrict__ xy
             amax = fmaxf(amax, fmaxf(fabsf(s_red[0][a]), fabsf(s_red[0][3 + a])));
         }
         for (int a = 0; a < 3; ++a) vol *= fmaxf(ext[a], 1e-3f * big + 1e-20f);   // flat clouds: the thin axis gets one cell
-        float h = cbrtf(kCellOcc * vol / (float)N);
+        float h = cbrtf(occ * vol / (float)N);
         h = fmaxf(h, big / (float)kMaxGridDim + 1e-30f);
         for (;;) {   // respect the cell budget
             long long cells = 1;
@@ -256,10 +262,10 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn_grid(const float* __restric
     int c[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) c[a] = cell_coord(qv[a], gp.gmin[a], gp.inv_h[a], gp.G[a]);
-    float bd = lane < k ? INFINITY : -INFINITY;
-    int bi = lane < k ? 0x7fffffff - lane : -1;   // distinct sentinels: exactly one lane is "the worst"
+    float bd = INFINITY;                 // sorted list of (distance, id): +inf sentinels with ascending ids
+    int bi = 0x7fffff00 + lane;
     float tau = INFINITY;
-    int tau_i = 0x7fffffff;
+    int tau_i = 0x7fffff00 + k - 1;
     auto scan = [&](int begin, int end) {   // score the sorted range [begin, end)
         for (int i0 = begin; i0 < end; i0 += 32) {
             const int i = i0 + lane;
@@ -270,7 +276,7 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn_grid(const float* __restric
                 id = __ldg(I + i);
             }
             const unsigned cand = __ballot_sync(kFull, i < end && !worse(d, id, tau, tau_i));
-            insert_candidates(cand, d, id, bd, bi, tau, tau_i);
+            insert_candidates(cand, d, id, bd, bi, tau, tau_i, k);
         }
     };
     const int rmax = max(max(gp.G[0], gp.G[1]), gp.G[2]);
@@ -333,7 +339,9 @@ extern "C" int pvraft_knn_fwd(const float* xyz, const float* query, int B, int N
         const size_t smem = (size_t)NP * sizeof(unsigned long long);
         int rc;
         if ((rc = opt_in_smem(k_grid_sort, smem))) return rc;
-        k_grid_sort<<<B, 1024, smem, st>>>(xyz, N, NP, params, sorted, ids, keys);
+        float occ = kCellOcc;
+        if (const char* e = getenv("PVRAFT_KNN_OCC")) { const float v = (float)atof(e); if (v > 0.f) occ = v; }
+        k_grid_sort<<<B, 1024, smem, st>>>(xyz, N, NP, occ, params, sorted, ids, keys);
         if ((rc = check_launch("knn grid sort"))) return rc;
         k_grid_cells<<<dim3((kMaxCells + 1 + 255) / 256, B), 256, 0, st>>>(keys, N, cell_start);
         if ((rc = check_launch("knn grid cells"))) return rc;
