@@ -97,9 +97,10 @@ PVRAFT_API int pvraft_corr_reorder(const float* val_in, const int32_t* idx_in, i
  *                                (distance = (dx*dx+dy*dy)+dz*dz, no FMA); order within a point is
  *                                unspecified; exact-distance ties at the 32nd place are broken deterministically
  *   -> knn_slot [B,N,32] int32   candidate slot (0..K-1) of each selected neighbour; may be NULL
- *   -> moments  [B,16] double    ACCUMULATED first/second moments of the 4-vector over the sample's
- *                                N*32 edges: [0..3]=sum f_i, [4..13]=sum f_i f_j (i<=j, row-major
- *                                upper triangle), [14]=edge count; may be NULL
+ *   -> moments  [B,16] double    first/second moments of the 4-vector over the sample's N*32 edges, accumulated with
+ *                                atomics into a buffer the caller has ZEROED: [0..3]=sum f_i, [4..13]=sum f_i f_j (i<=j,
+ *                                row-major upper triangle), [14]=edge count, [15]=scratch (the kernel's work counter);
+ *                                may be NULL (then the points are split statically)
  *   -> dbg_cube [B,N,K,levels] int8  cell id or -1 of every candidate (test hook; NULL in production)
  * K in {32,64,128,256,512,1024}; 1 <= levels <= 4; knn fixed at 32.
  * --------------------------------------------------------------------------------------------- */

@@ -159,13 +159,25 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
+    // Work distribution.  With a moment buffer (zeroed by the caller) and at least one CTA per sample, the CTAs of a sample
+    // share its points dynamically: warps claim chunks of 8 consecutive points from a counter kept in the unused 16th moment
+    // slot (the per-point cost varies ~2x with the local density, and a cloud's points are usually stored region by region,
+    // so equal contiguous shares left ~20 % of the SM time idle).  Otherwise: equal contiguous shares of B*N.
+    const bool dyn = p.moments != nullptr && (int)gridDim.x >= p.B;
     const long long total = (long long)p.B * p.N;
     long long pt_begin, pt_end;
-    split_range(total, gridDim.x, blockIdx.x, pt_begin, pt_end);
+    if (dyn) {
+        const int b = (int)((long long)blockIdx.x * p.B / gridDim.x);
+        pt_begin = (long long)b * p.N;
+        pt_end = pt_begin + p.N;
+    } else {
+        split_range(total, gridDim.x, blockIdx.x, pt_begin, pt_end);
+    }
     const int L = p.levels;
     const float rc = L == 1 ? p.r[0] : L == 2 ? p.r[1] : L == 3 ? p.r[2] : p.r[3];               // coarsest level
     const float inv_rc = L == 1 ? p.inv_r[0] : L == 2 ? p.inv_r[1] : L == 3 ? p.inv_r[2] : p.inv_r[3];
     unsigned phase0 = 0, phase1 = 0;
+    constexpr int kChunk = 8;
 
     long long seg = pt_begin;
     while (seg < pt_end) {
@@ -173,13 +185,23 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
         long long seg_end = (long long)(b + 1) * p.N;
         if (seg_end > pt_end) seg_end = pt_end;
         const float* tab_g = p.xyz2 + (size_t)b * p.N * 3;
+        int* counter = dyn ? reinterpret_cast<int*>(p.moments + (size_t)b * PVRAFT_MOMENTS + 15) : nullptr;
+        auto claim_chunk = [&]() -> long long {   // first point of the next unclaimed chunk of this sample
+            int c = 0;
+            if (lane == 0) c = atomicAdd(counter, kChunk);
+            return seg + __shfl_sync(kFull, c, 0);
+        };
+        // this warp's first two points
+        long long pt0 = seg + w, nxt0 = seg + w + p.warps;
+        int left0 = 0;   // points after nxt0 that remain in nxt0's chunk (dynamic mode)
+        if (dyn && active_warp) { pt0 = claim_chunk(); nxt0 = pt0 + 1; left0 = kChunk - 2; }
         // kick off this warp's first row, then stage the sample's xyz table while it is in flight
-        if (active_warp && seg + w < seg_end) {
+        if (active_warp && pt0 < seg_end) {
             if (lane == 0) {
                 mbar_expect_tx(s_bar, K * 4);
-                bulk_g2s(s_stage, p.corr_idx + (seg + w) * K, K * 4, s_bar);
+                bulk_g2s(s_stage, p.corr_idx + pt0 * K, K * 4, s_bar);
             }
-            prefetch_row(p.corr_val + (seg + w) * K, K, lane);
+            prefetch_row(p.corr_val + pt0 * K, K, lane);
         }
         __syncthreads();   // previous segment's readers are done (table and point counter)
         if (threadIdx.x == 0) s_next = 2 * p.warps;   // warp w starts with points w and w + warps
@@ -192,9 +214,9 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
         for (int i = 0; i < 14; ++i) mom[i] = 0.0;
 
         if (active_warp) {
-            int cur = 0;
-            long long nxt = seg + w + p.warps;   // the second point of this warp is fixed as well; later ones are claimed
-            for (long long pt = seg + w; pt < seg_end; cur ^= 1) {
+            int cur = 0, left = left0, done = 0;
+            long long nxt = nxt0;
+            for (long long pt = pt0; pt < seg_end; cur ^= 1, ++done) {
                 const float cx = __ldg(p.coords + pt * 3 + 0);
                 const float cy = __ldg(p.coords + pt * 3 + 1);
                 const float cz = __ldg(p.coords + pt * 3 + 2);
@@ -417,11 +439,15 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                     mom[11] += f2 * f2; mom[12] += f2 * f3; mom[13] += f3 * f3;
                 }
                 __syncwarp();
-                // claim the point after next (its row is fetched while `nxt` is processed)
+                // the point after next (its row is fetched while `nxt` is processed)
                 pt = nxt;
-                int claim = 0;
-                if (lane == 0) claim = atomicAdd(&s_next, 1);
-                nxt = seg + __shfl_sync(kFull, claim, 0);
+                if (dyn) {
+                    if (left > 0) { ++nxt; --left; } else { nxt = claim_chunk(); left = kChunk - 1; }
+                } else {
+                    int claim = 0;
+                    if (lane == 0) claim = atomicAdd(&s_next, 1);
+                    nxt = seg + __shfl_sync(kFull, claim, 0);
+                }
             }
             if (p.moments) {
 #pragma unroll 1
@@ -432,8 +458,7 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                     const double s = warp_sum(v);
                     if (lane == 0 && s != 0.0) atomicAdd(p.moments + (size_t)b * PVRAFT_MOMENTS + i, s);
                 }
-                if (lane == 0 && w == 0)
-                    atomicAdd(p.moments + (size_t)b * PVRAFT_MOMENTS + 14, (double)(seg_end - seg) * 32.0);
+                if (lane == 0 && done > 0) atomicAdd(p.moments + (size_t)b * PVRAFT_MOMENTS + 14, (double)done * 32.0);
             }
         }
         seg = seg_end;
