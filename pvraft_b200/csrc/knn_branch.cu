@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(kKbThreads) k_knn_branch(const pvraft_knn_bran
     __shared__ __align__(16) float s_wf[4 * 64];     // conv_flow, [i][c] (i < 3)
     __shared__ __align__(16) float s_bf[64];
     __shared__ double s_kn[64 * 2];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel's prologue may overlap this kernel's tail
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int tiles_per_sample = (a.N + kKbTile - 1) / kKbTile;
     const int n_tiles = a.B * tiles_per_sample;

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge_pairs(const float
                                                                      float* __restrict__ ymin, double* __restrict__ stats) {
     __shared__ double s_part[kEdgeThreads / 32][128][2];
     __shared__ __align__(16) float4 s_edge[kEdgeThreads / 32][32];   // (neighbour id bits, ex, ey, ez) of the warp's point
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel's prologue may overlap this kernel's tail
     const int lane = lane_id(), w = warp_id(), nwarps = kEdgeThreads / 32;
     const int ld = cin + 3;
     float2 wx[PAIRS], wy[PAIRS], wz[PAIRS];

@@ -406,6 +406,10 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tsu32(&s_tmem_base)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // Programmatic dependent launch: everything above (shared-memory carve-up, barrier init, TMEM allocation, descriptor
+    // prefetch) may overlap the tail of the previous kernel on this stream; every global read is below this line.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (warp >= 10) {
         for (int c = threadIdx.x - 320; c < p.N; c += 256) {
             s_bias[c] = (p.bias != nullptr && c < p.cout) ? __ldg(p.bias + c) : 0.f;
@@ -707,6 +711,19 @@ extern "C" int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream
     if ((rc = opt_in_smem(k_tc_linear, smem))) return rc;
     const long long n_tiles = (M + kTcM - 1) / kTcM;
     const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
-    k_tc_linear<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(mw_hi, mw_lo, ma[0], ma[1], ma[2], mmin, p);
+    // launched with programmatic stream serialization: the kernel's prologue may start while the previous kernel drains
+    static const bool pdl = []() { const char* e = getenv("PVRAFT_TC_PDL"); return !(e && atoi(e) == 0); }();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, k_tc_linear, mw_hi, mw_lo, ma[0], ma[1], ma[2], mmin, p);
+    if (le != cudaSuccess) return fail((int)le, "tc_linear: launch failed: %s", cudaGetErrorString(le));
     return check_launch("tc_linear");
 }
