@@ -148,7 +148,8 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
     uint2* s_chunk = reinterpret_cast<uint2*>(wbase + K * 8 + VL);       // [32]  (cell codes, corr) of one chunk
     int* s_slots = reinterpret_cast<int*>(wbase + K * 8 + VL + 256);     // [32]  kNN slots
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(wbase + K * 8 + VL + 384);   // [2]
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel's prologue may overlap this kernel's tail
+    pdl_trigger();   // the next kernel may be staged while this one drains
+    pdl_wait();      // (launched with PDL: nothing above touches global memory)
     const bool active_warp = w < p.warps;
     __shared__ int s_next;   // next unclaimed point of the current segment (warps take points dynamically: per-point cost varies)
     // 1/c in double for c = 0..K: (float)(double(sum) * rcp[c]) is the correctly rounded fp32 quotient sum/c for
@@ -560,11 +561,11 @@ static int launch_lookup(LookupParams& p, cudaStream_t st) {
     if (smem_tab) {
         auto k = k_corr_lookup<KPL, POW2, true>;
         if ((rc = opt_in_smem(k, smem))) return rc;
-        k<<<grid, kLookupThreads, smem, st>>>(p);
+        launch_pdl(k, grid, kLookupThreads, smem, st, p);
     } else {
         auto k = k_corr_lookup<KPL, POW2, false>;
         if ((rc = opt_in_smem(k, smem))) return rc;
-        k<<<grid, kLookupThreads, smem, st>>>(p);
+        launch_pdl(k, grid, kLookupThreads, smem, st, p);
     }
     return check_launch("corr_lookup");
 }

@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(kKbThreads) k_knn_branch(const pvraft_knn_bran
     __shared__ __align__(16) float s_wf[4 * 64];     // conv_flow, [i][c] (i < 3)
     __shared__ __align__(16) float s_bf[64];
     __shared__ double s_kn[64 * 2];
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel's prologue may overlap this kernel's tail
+    pdl_trigger();   // the next kernel may be staged while this one drains
+    pdl_wait();      // (launched with PDL: nothing above touches global memory)
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int tiles_per_sample = (a.N + kKbTile - 1) / kKbTile;
     const int n_tiles = a.B * tiles_per_sample;
@@ -185,7 +186,7 @@ extern "C" int pvraft_knn_branch_fwd(const pvraft_knn_branch_args* a, void* stre
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_knn_branch<false>, kKbThreads, 0);
     const long long cap = (long long)sm_count() * (per_sm > 0 ? per_sm : 1);
     const int grid = (int)(n_tiles < cap ? n_tiles : cap);
-    if (slope <= 1.f) k_knn_branch<true><<<grid, kKbThreads, 0, (cudaStream_t)stream>>>(*a);
-    else k_knn_branch<false><<<grid, kKbThreads, 0, (cudaStream_t)stream>>>(*a);
+    if (slope <= 1.f) launch_pdl(k_knn_branch<true>, grid, kKbThreads, 0, (cudaStream_t)stream, *a);
+    else launch_pdl(k_knn_branch<false>, grid, kKbThreads, 0, (cudaStream_t)stream, *a);
     return check_launch("knn_branch");
 }

@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge_pairs(const float
                                                                      float* __restrict__ ymin, double* __restrict__ stats) {
     __shared__ double s_part[kEdgeThreads / 32][128][2];
     __shared__ __align__(16) float4 s_edge[kEdgeThreads / 32][32];   // (neighbour id bits, ex, ey, ez) of the warp's point
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel's prologue may overlap this kernel's tail
+    pdl_trigger();   // the next kernel may be staged while this one drains
+    pdl_wait();      // (launched with PDL: nothing above touches global memory)
     const int lane = lane_id(), w = warp_id(), nwarps = kEdgeThreads / 32;
     const int ld = cin + 3;
     float2 wx[PAIRS], wy[PAIRS], wz[PAIRS];
@@ -172,11 +173,11 @@ extern "C" int pvraft_setconv_edge_fwd(const float* fc1p, const int32_t* nbr, co
     const int grid = (int)(g < 1 ? 1 : g);
     cudaStream_t st = (cudaStream_t)stream;
     if (C <= 64) {
-        k_setconv_edge_pairs<1><<<grid, kEdgeThreads, 0, st>>>(fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats);
+        launch_pdl(k_setconv_edge_pairs<1>, grid, kEdgeThreads, 0, st, fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats);
         return check_launch("setconv_edge");
     }
     if (C <= 128) {
-        k_setconv_edge_pairs<2><<<grid, kEdgeThreads, 0, st>>>(fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats);
+        launch_pdl(k_setconv_edge_pairs<2>, grid, kEdgeThreads, 0, st, fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats);
         return check_launch("setconv_edge");
     }
     return fail(PVRAFT_ERR_UNSUPPORTED, "setconv_edge: C=%d", C);
