@@ -337,7 +337,7 @@ class _QuietStdout:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', choices=['native', 'reference'], default='native')
     ap.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='samples per GPU')
