@@ -6,6 +6,8 @@ The loop body keeps every tensor point-major on the device, launches a fixed seq
 per iteration with no host synchronisation, and fuses the RAFT glue (flow = coords2 - coords1,
 coords2 += delta, model/RAFTSceneFlow.py:41-46) into the first / last kernel of the iteration.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -24,6 +26,47 @@ def _require_inference(module):
 
 
 class _RaftBase(nn.Module):
+    # CUDA-graph replay of the whole forward (encoders, correlation build, all iterations): the eager path costs ~28 us of
+    # host time per launch (python + ctypes + tensor-map encodes), which bounds small batches (B <= 2: ~0.5 ms per
+    # iteration).  Opt-in: `model.use_cuda_graph = True` or PVRAFT_CUDA_GRAPH=1.  One graph per (B, N, num_iters); inputs are
+    # copied into the graph's static buffers, outputs are returned as copies.  Parameters are read at capture time through
+    # their device pointers, so in-place weight updates are seen by replays; replaced weight tensors need `reset_graphs()`.
+    use_cuda_graph = os.environ.get('PVRAFT_CUDA_GRAPH', '0') == '1'
+
+    def reset_graphs(self):
+        self.__dict__.pop('_graphs', None)
+
+    def _graphed(self, p, num_iters):
+        xyz1, xyz2 = p[0].detach().contiguous().float(), p[1].detach().contiguous().float()
+        graphs = self.__dict__.setdefault('_graphs', {})
+        key = (tuple(xyz1.shape), xyz1.device, int(num_iters))
+        entry = graphs.get(key)
+        if entry is None:
+            static_in = [torch.empty_like(xyz1), torch.empty_like(xyz2)]
+            static_in[0].copy_(xyz1)
+            static_in[1].copy_(xyz2)
+            side = torch.cuda.Stream(device=xyz1.device)   # warm-up off the capture stream: weight splits, derived constants
+            side.wait_stream(torch.cuda.current_stream(xyz1.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._forward_impl(static_in, num_iters)
+            torch.cuda.current_stream(xyz1.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._forward_impl(static_in, num_iters)
+            entry = graphs[key] = (graph, static_in, static_out)
+        graph, static_in, static_out = entry
+        static_in[0].copy_(xyz1)
+        static_in[1].copy_(xyz2)
+        graph.replay()
+        return static_out.clone() if torch.is_tensor(static_out) else [t.clone() for t in static_out]
+
+    def forward(self, p, num_iters=12):
+        _require_inference(self)
+        if self.use_cuda_graph and p[0].is_cuda:
+            return self._graphed(p, num_iters)
+        return self._forward_impl(p, num_iters)
+
     def _encode(self, p):
         xyz1, xyz2 = p[0], p[1]
         if xyz1.dim() != 3 or xyz1.shape[-1] != 3 or xyz1.shape != xyz2.shape:
@@ -83,8 +126,7 @@ class RSF(_RaftBase):
                                     resolution=3, truncate_k=args.truncate_k)
         self.update_block = UpdateBlock(hidden_dim=self.hidden_dim)
 
-    def forward(self, p, num_iters=12):
-        _require_inference(self)
+    def _forward_impl(self, p, num_iters=12):
         xyz1, _, _, graph_context, net, inp = self._encode(p)
         _, preds = self._iterate(xyz1, graph_context, net, inp, num_iters, keep_all=True)
         return preds
@@ -102,8 +144,7 @@ class RSF_refine(_RaftBase):
         self.update_block = UpdateBlock(hidden_dim=self.hidden_dim)
         self.refine_block = FlotRefine()
 
-    def forward(self, p, num_iters=12):
-        _require_inference(self)
+    def _forward_impl(self, p, num_iters=12):
         xyz1, _, graph, graph_context, net, inp = self._encode(p)
         flow, _ = self._iterate(xyz1, graph_context, net, inp, num_iters, keep_all=False)
         return self.refine_block(flow, graph)                            # RAFTSceneFlowRefine.py:46

@@ -14,10 +14,12 @@ from pvraft_b200 import RSF, ops  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=8)
 ap.add_argument('--iters', type=int, default=32)
+ap.add_argument('--graph', action='store_true', help='replay the forward as one CUDA graph')
 a = ap.parse_args()
 dev = torch.device('cuda:0')
 torch.manual_seed(0)
 model = RSF(bench.make_args()).to(dev).eval()
+model.use_cuda_graph = a.graph
 pc1, pc2 = [t.to(dev) for t in bench.synthetic_clouds(a.batch, bench.N_POINTS, 1234)]
 with torch.no_grad():
     for _ in range(2):
