@@ -14,6 +14,7 @@ import torch.nn as nn
 from . import ops
 from .corr import CorrBlock
 from .extractor import FlotEncoder
+from .graph import Graph
 from .refine import FlotRefine
 from .update import UpdateBlock
 
@@ -73,8 +74,13 @@ class _RaftBase(nn.Module):
             raise ValueError('expected p = [xyz1 [B,N,3], xyz2 [B,N,3]]')
         xyz1 = xyz1.detach().contiguous().float()
         xyz2 = xyz2.detach().contiguous().float()
-        fmap1, graph = self.feature_extractor(xyz1, point_major=True)    # RAFTSceneFlow.py:25
-        fmap2, _ = self.feature_extractor(xyz2, point_major=True)        # :26
+        # both clouds go through the shared feature encoder as one batch of 2B samples (RAFTSceneFlow.py:25-26: every op is
+        # per sample): half the launches, and 2B*N/128 tiles fill the 148 SMs more evenly
+        b = xyz1.shape[0]
+        both = torch.cat([xyz1, xyz2], 0)
+        fmap, graph2 = self.feature_extractor(both, point_major=True)
+        fmap1, fmap2 = fmap[:b], fmap[b:]
+        graph = Graph(graph2.nbr[:b], graph2._rel[:b], graph2.k_neighbors, [b * xyz1.shape[1]] * 2)   # pc1's graph
         self.corr_block.init_module_pm(fmap1, fmap2, xyz2)               # :29
         # the reference rebuilds the same pc1 graph for the context encoder (:31); reuse it
         fct1, graph_context = self.context_extractor(xyz1, graph=graph, point_major=True)
