@@ -240,6 +240,10 @@ __global__ void __launch_bounds__(kTopkThreads) k_corr_topk_vec(const float* __r
             if (ww < w) before[i] += a;
         }
     }
+    // Only ~K/M of the keys are kept: a float4 group without any key >= T (3 in 4 groups at K/M = 1/16) is skipped on its
+    // packed counts alone, and the surviving groups store through a per-row base pointer.
+    float* vrow = val + row * (size_t)K;
+    int32_t* irow = idx + row * (size_t)K;
     int base_gt = 0, base_eq = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -248,6 +252,8 @@ __global__ void __launch_bounds__(kTopkThreads) k_corr_topk_vec(const float* __r
         int eq_before = base_eq + (int)((before[3 + j / 3] >> sh) & 0x7FFu);
         base_gt += (int)((tot[j / 3] >> sh) & 0x7FFu);
         base_eq += (int)((tot[3 + j / 3] >> sh) & 0x7FFu);
+        const unsigned mine = ((cnt[j / 3] >> sh) | (cnt[3 + j / 3] >> sh)) & 0x7FFu;   // any key >= T in this group?
+        if (mine == 0u) continue;
         const int col = (j * kTopkThreads + tid) * 4;
         const uint4 kk = s_key[j * kTopkThreads + tid];
         const unsigned ke[4] = {kk.x, kk.y, kk.z, kk.w};
@@ -256,9 +262,9 @@ __global__ void __launch_bounds__(kTopkThreads) k_corr_topk_vec(const float* __r
             const unsigned key = ke[e];
             const bool gt = key > T, eq = key == T;
             if (gt || (eq && eq_before < need_eq)) {
-                const size_t pos = row * (size_t)K + (size_t)(gt_before + min(eq_before, need_eq));
-                val[pos] = key2f(key);
-                idx[pos] = col + e;
+                const int pos = gt_before + min(eq_before, need_eq);
+                vrow[pos] = key2f(key);
+                irow[pos] = col + e;
             }
             gt_before += gt ? 1 : 0;
             eq_before += eq ? 1 : 0;
