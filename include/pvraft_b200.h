@@ -183,7 +183,9 @@ typedef struct pvraft_tc_linear_args {
     const float* bias;      /* [cout] or NULL (GRU_ZR: bias of z; GRU_Q: bias of q) */
     const float* bias2;     /* GRU_ZR: bias of r */
     int out_act;
-    const float* residual;  /* [B,N,cout] or NULL */
+    const float* residual;  /* PLAIN: [B,N,cout] added to the output, or NULL.  GRU epilogues: per-point term added to the
+                               pre-activations ([B,N,128] = [z|r] for GRU_ZR, [B,N,64] for GRU_Q) -- the contribution of the
+                               context features, constant over the RAFT iterations -- or NULL */
     float* out;             /* [B,N,cout] */
     float* out2;            /* GRU_ZR: r*h [B,N,64] */
     const float* h;         /* GRU epilogues: previous hidden state [B,N,64] */

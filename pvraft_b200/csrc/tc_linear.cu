@@ -267,8 +267,14 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 hv = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)row * 64 + c + q * 4));
-                const float4 bz = *reinterpret_cast<const float4*>(s_bias + c + q * 4);
-                const float4 br = *reinterpret_cast<const float4*>(s_bias + p.N + c + q * 4);
+                float4 bz = *reinterpret_cast<const float4*>(s_bias + c + q * 4);
+                float4 br = *reinterpret_cast<const float4*>(s_bias + p.N + c + q * 4);
+                if (p.residual != nullptr) {   // per-point pre-activation term [M,128] = [z | r] (the constant context part)
+                    const float4 az = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * 128 + c + q * 4));
+                    const float4 ar = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * 128 + 64 + c + q * 4));
+                    bz.x += az.x; bz.y += az.y; bz.z += az.z; bz.w += az.w;
+                    br.x += ar.x; br.y += ar.y; br.z += ar.z; br.w += ar.w;
+                }
                 z[q * 4 + 0] = tsigmoid(__uint_as_float(vz[q * 4 + 0]) + bz.x); z[q * 4 + 1] = tsigmoid(__uint_as_float(vz[q * 4 + 1]) + bz.y);
                 z[q * 4 + 2] = tsigmoid(__uint_as_float(vz[q * 4 + 2]) + bz.z); z[q * 4 + 3] = tsigmoid(__uint_as_float(vz[q * 4 + 3]) + bz.w);
                 rh[q * 4 + 0] = tsigmoid(__uint_as_float(vr[q * 4 + 0]) + br.x) * hv.x; rh[q * 4 + 1] = tsigmoid(__uint_as_float(vr[q * 4 + 1]) + br.y) * hv.y;
@@ -326,7 +332,11 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
             for (int q = 0; q < 4; ++q) {
                 const float4 hv = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)row * 64 + c + q * 4));
                 const float4 zv = __ldg(reinterpret_cast<const float4*>(p.z + (size_t)row * 64 + c + q * 4));
-                const float4 bq = *reinterpret_cast<const float4*>(s_bias + c + q * 4);
+                float4 bq = *reinterpret_cast<const float4*>(s_bias + c + q * 4);
+                if (p.residual != nullptr) {   // per-point pre-activation term [M,64]
+                    const float4 aq = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * 64 + c + q * 4));
+                    bq.x += aq.x; bq.y += aq.y; bq.z += aq.z; bq.w += aq.w;
+                }
                 o[q * 4 + 0] = (1.f - zv.x) * hv.x + zv.x * tanhf(__uint_as_float(vq[q * 4 + 0]) + bq.x);
                 o[q * 4 + 1] = (1.f - zv.y) * hv.y + zv.y * tanhf(__uint_as_float(vq[q * 4 + 1]) + bq.y);
                 o[q * 4 + 2] = (1.f - zv.z) * hv.z + zv.z * tanhf(__uint_as_float(vq[q * 4 + 2]) + bq.z);
@@ -661,9 +671,9 @@ extern "C" int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream
     if (a->in_min && !a->in_stats) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: in_min needs the GroupNorm prologue");
     if (a->out_stats && (a->epilogue != TC_EPI_PLAIN || a->cout % PVRAFT_GN_GROUPS || (a->cout / PVRAFT_GN_GROUPS) % 4)) return fail(PVRAFT_ERR_UNSUPPORTED, "tc_linear: out_stats needs a GroupNorm group size that is a multiple of 4 (cout=%d)", a->cout);
     if (a->epilogue < TC_EPI_PLAIN || a->epilogue > TC_EPI_FLOW) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: unknown epilogue %d", a->epilogue);
-    if ((a->epilogue == TC_EPI_GRU_ZR || a->epilogue == TC_EPI_GRU_Q) && (a->cout != 64 || !a->h || !a->bias)) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: GRU epilogues need cout=64, h and bias");
+    if ((a->epilogue == TC_EPI_GRU_ZR || a->epilogue == TC_EPI_GRU_Q) && (a->cout != 64 || !a->h || (!a->bias && !a->residual))) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: GRU epilogues need cout=64, h and a bias or a pre-activation term");
     if (a->epilogue == TC_EPI_FLOW && (a->cout != 64 || a->n_pad != 64 || !a->bias || !a->w3 || !a->b3 || (a->coords2_out && !a->coords2) || (a->flow_out && (!a->coords2_out || !a->coords1)))) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: flow epilogue needs cout = n_pad = 64, bias, w3, b3 and consistent coordinate pointers");
-    if (a->epilogue == TC_EPI_GRU_ZR && (a->n_pad != 128 || !a->bias2 || !a->out2)) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: GRU zr epilogue needs n_pad=128, bias2, out2");
+    if (a->epilogue == TC_EPI_GRU_ZR && (a->n_pad != 128 || (!a->bias2 && !a->residual) || !a->out2)) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: GRU zr epilogue needs n_pad=128, bias2, out2");
     if (a->epilogue == TC_EPI_GRU_Q && (a->n_pad != 64 || !a->z)) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: GRU q epilogue needs n_pad=64 and z");
     const long long M = (long long)a->B * a->N;
     TcParams p{};
@@ -700,7 +710,7 @@ extern "C" int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream
     const int stages_res = w_all < budget ? (int)((budget - w_all) / a_stage) : 0;
     const int stages_str = (int)(budget / (a_stage + w_kb));
     p.w_resident = (stages_res >= 3 || stages_res >= stages_str) ? 1 : 0;
-    if (const char* e = getenv("PVRAFT_TC_WRES")) p.w_resident = (atoi(e) != 0 && stages_res >= 1) ? 1 : 0;
+    if (const char* e = getenv("PVRAFT_TC_WRES")) p.w_resident = (atoi(e) != 0 && stages_res >= 2) ? 1 : 0;   // (debug override)
     int stages = p.w_resident ? stages_res : stages_str;
     stages = stages < 1 ? 1 : (stages > kTcMaxStages ? kTcMaxStages : stages);
     const size_t stage = a_stage + (p.w_resident ? 0 : w_kb);
