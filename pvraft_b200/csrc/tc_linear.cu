@@ -715,6 +715,7 @@ extern "C" int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream
     stages = stages < 1 ? 1 : (stages > kTcMaxStages ? kTcMaxStages : stages);
     const size_t stage = a_stage + (p.w_resident ? 0 : w_kb);
     if (const char* e = getenv("PVRAFT_TC_STAGES")) { const int v = atoi(e); if (v >= 1 && v <= stages) stages = v; }
+    if (stages < 2) return fail(PVRAFT_ERR_SMEM, "tc_linear: K=%d, n_pad=%d leave room for only %d operand stage(s) (2 needed)", K, a->n_pad, stages);
     p.stages = stages;
     if (const char* e = getenv("PVRAFT_TC_DBG")) p.dbg = atoi(e);
     const size_t smem = stages * stage + (p.w_resident ? w_all : 0) + fixed;
