@@ -1,6 +1,7 @@
 """Build libpvraft_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so must travel with the
 repo snapshot to the GPU box).  `python -m pvraft_b200.build [--force]`."""
 import os
+import shlex
 import subprocess
 import sys
 
@@ -38,7 +39,8 @@ def build(force=False, verbose=False):
     os.makedirs(os.path.join(HERE, 'build'), exist_ok=True)
     for src in SOURCES:
         obj = os.path.join(HERE, 'build', src.replace('.cu', '.o'))
-        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc] + NVCC_FLAGS + shlex.split(os.environ.get('PVRAFT_NVCC_FLAGS', '')) + (['-Xptxas', '-v'] if verbose else []) + \
+            ['-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

@@ -3,17 +3,23 @@
 //
 //   out[M x N] = epilogue( prologue(A)[M x K] . W[N x K]^T )          M = B*Npts points, N = cout, K = cin
 //
-// A CTA owns 128 consecutive points (= 128 TMEM lanes).  Per 32-channel k-block:
-//   warp 0      TMA: the raw fp32 activation box [128 x 32] (SWIZZLE_128B; up to three source tensors are
-//               concatenated along K, e.g. [h | inp | motion] for the GRU) and the pre-split weight boxes W_hi, W_lo
-//   warps 2-5   transform: every 16-byte chunk of the raw box gets the folded GroupNorm affine + activation of its
-//               channels (optionally choosing the max or the min input by the sign of the scale), is split into
-//               hi = tf32(x), lo = tf32(x - hi) and written to the hi / lo boxes AT THE SAME swizzled offset (the split
-//               is elementwise, so no swizzle arithmetic is needed); fence.proxy.async; arrive on the stage barrier
-//   warp 1      one lane issues A_hi.W_hi + A_lo.W_hi + A_hi.W_lo (3 x 4 tcgen05.mma.kind::tf32, K = 8 each) into TMEM
-//   warps 2-5   epilogue: tcgen05.ld (thread = point) -> bias / ReLU / residual / GRU gates -> global, GroupNorm
-//               (sum, sum^2) per group reduced in the warp and accumulated with double atomics
-// Replaces the k_linear / k_gru CUDA-core kernels whenever Npts % 128 == 0 and cin % 32 == 0.
+// Persistent kernel, one CTA (18 warps) per SM, tiles of 128 consecutive points (= 128 TMEM lanes), 32-channel k-blocks:
+//   warp 0       TMA producer: raw fp32 activation boxes [128 x 32] (SWIZZLE_128B; up to three source tensors concatenated
+//                along K, e.g. [h | inp | motion] for the GRU) into a ring of 2..6 stages; the pre-split weight boxes
+//                W_hi, W_lo once per CTA when they fit next to the ring, else with every k-block
+//   warps 2-9    transform, two groups on alternate k-blocks: every 16-byte chunk of the raw box gets the folded GroupNorm
+//                affine + activation of its channels (optionally choosing the max or the min input by the sign of the
+//                scale), is split into hi = tf32(x), lo = tf32(x - hi) and written in place / next to it AT THE SAME swizzled
+//                offset (the split is elementwise); fence.proxy.async; one mbarrier arrival per warp
+//   warp 1       MMA issuer (the warp walks the loop, one elected lane issues): A_hi.W_hi + A_lo.W_hi + A_hi.W_lo =
+//                3 x 4 tcgen05.mma.kind::tf32 (K = 8 each) per k-block into one of two TMEM accumulators
+//   warps 10-17  epilogue, two per TMEM lane quadrant, one accumulator behind the MMA: tcgen05.ld -> bias / activation /
+//                residual -> transpose through shared memory -> coalesced stores; GroupNorm (sum, sum^2) of the output
+//                combined across the warps into one double atomic per (group, moment) and tile; ConvGRU-gate, cat-tail and
+//                flow-head (64 -> 3 + RAFT coordinate update) variants
+// Launched with programmatic stream serialization: the prologue overlaps the previous kernel's tail (griddepcontrol.wait
+// precedes the first global read).  Replaces the k_linear / k_gru / k_corrfeat / k_flowout CUDA-core kernels whenever
+// Npts % 128 == 0 and every source has a multiple of 32 channels.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -26,8 +32,15 @@ constexpr int kTcM = 128, kTcKB = 32;
 constexpr int kTcABytes = kTcM * kTcKB * 4;   // 16 KB: one activation box
 constexpr int kTcMaxStages = 6;
 
-__device__ unsigned long long g_tc_clock[64];   // debug timeline of CTA 0 (env PVRAFT_TC_DBG=1)
+// In-kernel timeline of CTA 0 (how the pipeline was tuned, tools/tc_clock.py): compiled in only with -DPVRAFT_TC_TIMELINE
+// and then recorded when PVRAFT_TC_DBG=1; the product build carries none of it.
+#ifdef PVRAFT_TC_TIMELINE
+__device__ unsigned long long g_tc_clock[64];
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TC_MARK(cond, slot) do { if (clk && (cond)) g_tc_clock[(slot)] = gtimer(); } while (0)
+#else
+#define TC_MARK(cond, slot) do { } while (0)
+#endif
 
 enum TcEpilogue { TC_EPI_PLAIN = 0, TC_EPI_GRU_ZR = 1, TC_EPI_GRU_Q = 2, TC_EPI_FLOW = 3 };
 
@@ -347,14 +360,6 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
     }
 }
 
-// Persistent, warp-specialised kernel:
-//   warp 0       weight producer (TMA boxes: once per CTA when the hi/lo weights fit in shared memory, else per k-block)
-//   warp 1       MMA issuer (one lane)
-//   warps 2-9    activation loaders + transform: coalesced 128-bit global loads of the raw fp32 rows (a 2-D TMA box of
-//                128-byte rows is served at ~1 us per 16 KB by the per-SM TMA unit, measured; plain LDG is ~8x faster),
-//                GroupNorm affine + activation, hi/lo split, stores at the SWIZZLE_128B offsets of the operand tiles;
-//                the loads of k-block i+1 are in flight while k-block i is transformed (double-buffered registers)
-//   warps 10-13  epilogue, one TMEM accumulator buffer behind the MMA
 // A CTA walks tiles blockIdx.x, +gridDim.x, ...; the operand ring and the two accumulators run across tile boundaries.
 constexpr int kTcXform = 256;   // transform threads
 
@@ -398,8 +403,10 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
     const int total_steps = my_tiles * num_kb;
     const unsigned acc_cols = p.N <= 32 ? 32u : p.N <= 64 ? 64u : 128u;   // columns per accumulator buffer
     const unsigned tmem_cols = acc_cols * 2;
+#ifdef PVRAFT_TC_TIMELINE
     const bool clk = p.dbg && blockIdx.x == 0;
-    if (clk && threadIdx.x == 0) g_tc_clock[0] = gtimer();
+#endif
+    TC_MARK(threadIdx.x == 0, 0);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w_hi) : "memory");
@@ -500,7 +507,7 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
                         }
                         tumma_commit(&s_empty[s]);
                         if (kb == num_kb - 1) tumma_commit(&s_acc_full[acc]);
-                        if (clk && step < 8) g_tc_clock[16 + step] = gtimer();
+                        TC_MARK(step < 8, 16 + step);
                     }
                     __syncwarp();
                 }
@@ -568,7 +575,7 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
             __syncwarp();
             if (lane == 0) tmbar_arrive(&s_ready[s]);   // one arrival per warp of the group
-            if (clk && t == 0 && step < 8) g_tc_clock[8 + step] = gtimer();
+            TC_MARK(t == 0 && step < 8, 8 + step);
             cp.next(num_kb, S);
             cp.next(num_kb, S);
         }
@@ -581,13 +588,13 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
             const unsigned acc_phase = (unsigned)(ti >> 1) & 1u;
             const int row0 = (blockIdx.x + ti * gridDim.x) * kTcM;
             tmbar_wait(&s_acc_full[acc], acc_phase);
-            if (clk && threadIdx.x == 320 && ti < 4) g_tc_clock[24 + ti] = gtimer();
+            TC_MARK(threadIdx.x == 320 && ti < 4, 24 + ti);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             tc_epilogue(p, tmem + (unsigned)acc * acc_cols, quad, half, lane, row0, row0 / p.pts_per_sample, s_bias, s_estage, s_part);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) tmbar_arrive(&s_acc_empty[acc]);   // one arrival per epilogue warp
-            if (clk && threadIdx.x == 320 && ti < 4) g_tc_clock[28 + ti] = gtimer();
+            TC_MARK(threadIdx.x == 320 && ti < 4, 28 + ti);
         }
     }
     __syncwarp();   // the producer / MMA roles run on one lane: re-converge those warps before the CTA-wide barrier
@@ -596,7 +603,7 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
     }
-    if (clk && threadIdx.x == 64) g_tc_clock[1] = gtimer();
+    TC_MARK(threadIdx.x == 64, 1);
 }
 
 // hi = tf32(w), lo = tf32(w - hi) of a [rows, ld] weight window [rows, cols] written as [rows_pad, cols_pad] (zero padded)
@@ -644,9 +651,11 @@ static int tc_make_map(CUtensorMap* m, const float* base, long long rows, int co
 
 using namespace pvraft;
 
+#ifdef PVRAFT_TC_TIMELINE
 extern "C" __attribute__((visibility("default"))) int pvraft_tc_debug_clock(unsigned long long* host64) {
     return (int)cudaMemcpyFromSymbol(host64, g_tc_clock, sizeof(unsigned long long) * 64);
 }
+#endif
 
 extern "C" int pvraft_tc_weight_split(const float* w, int rows, int cols, int ld, int col0, int rows_pad, int cols_pad, float* hi,
                                       float* lo, void* stream) {

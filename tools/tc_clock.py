@@ -1,3 +1,6 @@
+"""In-kernel globaltimer timeline of the tensor-core layer kernel (CTA 0).  Needs a library built with the timeline hooks:
+    PVRAFT_NVCC_FLAGS=-DPVRAFT_TC_TIMELINE python -m pvraft_b200.build --force   (then rebuild without it)
+    DBG=1 python tools/tc_clock.py"""
 import os, sys, ctypes as C
 os.environ['PVRAFT_TC_DBG'] = os.environ.get('DBG', '1')
 import torch
