@@ -2,11 +2,13 @@
 matches the reference's module surface, the product path has no CPU fallback, and the multi-process
 sharding logic works over gloo."""
 import ctypes
+
 import os
 import re
 import socket
 import types
 
+import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
@@ -143,3 +145,38 @@ def test_two_rank_gloo_shard_gather_and_timing():
     for r in range(world):
         ok, t, s = out[r]
         assert ok and t == 2.0 and s == 5.0
+
+
+def test_division_by_constant_sequence_is_exact():
+    """k_corr_gemm divides by sqrt(C) with q0 = x*r, q = q0 + (x - q0*s)*r, r = RN(1/s) (csrc/corr_gemm.cu: div_by_const).
+    Emulated here in numpy (an fp32 FMA = the double-precision product-sum rounded once to fp32): bit-identical to the true
+    fp32 division for every sampled x and every channel count the model can use."""
+    rng = np.random.default_rng(0)
+
+    def fma32(a, b, c):
+        return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+    for channels in (3, 32, 64, 96, 100, 128, 160, 256):
+        s = np.float32(np.sqrt(np.float32(channels)))
+        r = np.float32(1.0 / np.float64(s))
+        x = np.concatenate([rng.standard_normal(200_000).astype(np.float32) * np.float32(v) for v in (1e-3, 1.0, 50.0, 1e4)])
+        q0 = (x * r).astype(np.float32)
+        q = fma32(fma32(-q0, np.full_like(x, s), x), np.full_like(x, r), q0)
+        assert np.array_equal(q, (x / s).astype(np.float32)), channels
+
+
+def test_derived_cache_follows_parameter_versions():
+    from pvraft_b200 import ops
+    w = torch.nn.Parameter(torch.ones(4))
+    calls = []
+
+    def make(t):
+        calls.append(1)
+        return float(t.detach().sum())
+
+    assert ops.derived((w,), 'sum', make) == 4.0 and ops.derived((w,), 'sum', make) == 4.0 and len(calls) == 1
+    with torch.no_grad():
+        w.mul_(2.0)                                     # in-place update bumps the version -> re-derived
+    assert ops.derived((w,), 'sum', make) == 8.0 and len(calls) == 2
+    w.data = torch.full((4,), 3.0)                      # storage swap (e.g. module.to(device)) -> re-derived
+    assert ops.derived((w,), 'sum', make) == 12.0 and len(calls) == 3
