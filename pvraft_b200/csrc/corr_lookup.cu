@@ -149,7 +149,6 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
     int* s_slots = reinterpret_cast<int*>(wbase + K * 8 + VL + 256);     // [32]  kNN slots
     unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(wbase + K * 8 + VL + 384);   // [2]
     pdl_trigger();   // the next kernel may be staged while this one drains
-    pdl_wait();      // (launched with PDL: nothing above touches global memory)
     const bool active_warp = w < p.warps;
     __shared__ int s_next;   // next unclaimed point of the current segment (warps take points dynamically: per-point cost varies)
     // 1/c in double for c = 0..K: (float)(double(sum) * rcp[c]) is the correctly rounded fp32 quotient sum/c for
@@ -211,6 +210,10 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
             for (int i = threadIdx.x; i < p.N * 3; i += blockDim.x) s_tab[i] = __ldg(tab_g + i);
         }
         __syncthreads();
+        // Launched with PDL: everything above (reciprocal table, barriers, the sample's xyz table, the first candidate row)
+        // reads data that no kernel of the loop writes and may overlap the previous kernel's tail; the query coordinates
+        // below are written by the flow head, and the outputs may reuse memory the previous kernel still reads.
+        pdl_wait();
         double mom[14];
 #pragma unroll
         for (int i = 0; i < 14; ++i) mom[i] = 0.0;

@@ -50,7 +50,7 @@ __device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigne
 }
 
 template <int PAIRS>
-__global__ void __launch_bounds__(kEdgeThreads) k_setconv_edge_pairs(const float* __restrict__ fc1p, const int32_t* __restrict__ nbr,
+__global__ void __launch_bounds__(kEdgeThreads, PAIRS == 1 ? 6 : 4) k_setconv_edge_pairs(const float* __restrict__ fc1p, const int32_t* __restrict__ nbr,
                                                                      const float* __restrict__ edge_feats, const float* __restrict__ w_fc1,
                                                                      int cin, int B, int N, int C, float* __restrict__ ymax,
                                                                      float* __restrict__ ymin, double* __restrict__ stats) {

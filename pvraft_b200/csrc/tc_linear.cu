@@ -163,6 +163,23 @@ __device__ __forceinline__ void stage_store16(float* __restrict__ stg, int lane,
 #pragma unroll
     for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(gbase + (size_t)(j * 8 + rsub) * ld + cq * 4) = o[j];
 }
+// the inverse: a [32 rows x 16 columns] block of a row-major global tensor, loaded as 8 rows x 64 B per instruction and handed
+// to the thread that owns each row (thread-per-row loads would touch 32 sectors per instruction)
+__device__ __forceinline__ void stage_load16(float* __restrict__ stg, int lane, const float* __restrict__ gbase, int ld, float (&x)[16]) {
+    const int rsub = lane >> 2, cq = lane & 3;
+    float4 o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = __ldg(reinterpret_cast<const float4*>(gbase + (size_t)(j * 8 + rsub) * ld + cq * 4));
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(stg + (j * 8 + rsub) * kTcPitch16 + cq * 4) = o[j];
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(stg + lane * kTcPitch16 + q * 4);
+        x[q * 4 + 0] = v.x; x[q * 4 + 1] = v.y; x[q * 4 + 2] = v.z; x[q * 4 + 3] = v.w;
+    }
+}
 __device__ __forceinline__ bool telect_one() {
     unsigned pred;
     asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
@@ -276,10 +293,11 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
             unsigned vz[16], vr[16];
             tmem_ld16(tl + (unsigned)c, vz);
             tmem_ld16(tl + (unsigned)(64 + c), vr);
-            float z[16], rh[16];
+            float z[16], rh[16], hh[16];
+            stage_load16(stg, lane, p.h + (size_t)(row0 + quad * 32) * 64 + c, 64, hh);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float4 hv = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)row * 64 + c + q * 4));
+                const float4 hv = make_float4(hh[q * 4], hh[q * 4 + 1], hh[q * 4 + 2], hh[q * 4 + 3]);
                 float4 bz = *reinterpret_cast<const float4*>(s_bias + c + q * 4);
                 float4 br = *reinterpret_cast<const float4*>(s_bias + p.N + c + q * 4);
                 if (p.residual != nullptr) {   // per-point pre-activation term [M,128] = [z | r] (the constant context part)
@@ -340,11 +358,13 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
         for (int c = half * 32; c < half * 32 + 32; c += 16) {
             unsigned vq[16];
             tmem_ld16(tl + (unsigned)c, vq);
-            float o[16];
+            float o[16], hh[16], zz[16];
+            stage_load16(stg, lane, p.h + (size_t)(row0 + quad * 32) * 64 + c, 64, hh);
+            stage_load16(stg, lane, p.z + (size_t)(row0 + quad * 32) * 64 + c, 64, zz);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float4 hv = __ldg(reinterpret_cast<const float4*>(p.h + (size_t)row * 64 + c + q * 4));
-                const float4 zv = __ldg(reinterpret_cast<const float4*>(p.z + (size_t)row * 64 + c + q * 4));
+                const float4 hv = make_float4(hh[q * 4], hh[q * 4 + 1], hh[q * 4 + 2], hh[q * 4 + 3]);
+                const float4 zv = make_float4(zz[q * 4], zz[q * 4 + 1], zz[q * 4 + 2], zz[q * 4 + 3]);
                 float4 bq = *reinterpret_cast<const float4*>(s_bias + c + q * 4);
                 if (p.residual != nullptr) {   // per-point pre-activation term [M,64]
                     const float4 aq = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)row * 64 + c + q * 4));
