@@ -201,6 +201,9 @@ typedef struct pvraft_tc_linear_args {
     const float* coords2;   /* FLOW: [B,N,3] or NULL */
     float* coords2_out;     /* FLOW: [B,N,3] or NULL (may alias coords2) */
     float* flow_out;        /* FLOW: [B,N,3] or NULL */
+    float* flow_user;       /* FLOW: second copy of the flow, row r written at row row_map[r] ([B*N,3]) -- the caller's
+                               point order when the cloud was spatially reordered for locality -- or NULL */
+    const int32_t* row_map; /* FLOW: [B*N] destination rows of flow_user */
 } pvraft_tc_linear_args;
 
 PVRAFT_API int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream);

@@ -75,7 +75,8 @@ struct TcParams {
     int out_ld;               // row stride of `out` in floats (cout, or cout + 3 with a tail)
     const float* tail;        // [M,3] copied into output columns cout..cout+2, or nullptr
     const float *w3, *b3, *coords1, *coords2;   // FLOW epilogue
-    float *coords2_out, *flow_out;
+    float *coords2_out, *flow_out, *flow_user;
+    const int32_t* row_map;
 };
 
 __device__ __forceinline__ unsigned tsu32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -347,7 +348,11 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
                 if (p.coords2_out != nullptr) {
                     const float c2 = p.coords2[g] + dd[k];   // RAFTSceneFlow.py:45
                     p.coords2_out[g] = c2;
-                    if (p.flow_out != nullptr) p.flow_out[g] = c2 - __ldg(p.coords1 + g);   // RAFTSceneFlow.py:46
+                    if (p.flow_out != nullptr) {
+                        const float fl = c2 - __ldg(p.coords1 + g);   // RAFTSceneFlow.py:46
+                        p.flow_out[g] = fl;
+                        if (p.flow_user != nullptr) p.flow_user[(size_t)__ldg(p.row_map + row) * 3 + k] = fl;
+                    }
                 }
             }
         }
@@ -701,7 +706,7 @@ extern "C" int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream
     if (a->out_stats && (a->epilogue != TC_EPI_PLAIN || a->cout % PVRAFT_GN_GROUPS || (a->cout / PVRAFT_GN_GROUPS) % 4)) return fail(PVRAFT_ERR_UNSUPPORTED, "tc_linear: out_stats needs a GroupNorm group size that is a multiple of 4 (cout=%d)", a->cout);
     if (a->epilogue < TC_EPI_PLAIN || a->epilogue > TC_EPI_FLOW) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: unknown epilogue %d", a->epilogue);
     if ((a->epilogue == TC_EPI_GRU_ZR || a->epilogue == TC_EPI_GRU_Q) && (a->cout != 64 || !a->h || (!a->bias && !a->residual))) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: GRU epilogues need cout=64, h and a bias or a pre-activation term");
-    if (a->epilogue == TC_EPI_FLOW && (a->cout != 64 || a->n_pad != 64 || !a->bias || !a->w3 || !a->b3 || (a->coords2_out && !a->coords2) || (a->flow_out && (!a->coords2_out || !a->coords1)))) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: flow epilogue needs cout = n_pad = 64, bias, w3, b3 and consistent coordinate pointers");
+    if (a->epilogue == TC_EPI_FLOW && (a->cout != 64 || a->n_pad != 64 || !a->bias || !a->w3 || !a->b3 || (a->coords2_out && !a->coords2) || (a->flow_out && (!a->coords2_out || !a->coords1)) || (a->flow_user && (!a->flow_out || !a->row_map)))) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: flow epilogue needs cout = n_pad = 64, bias, w3, b3 and consistent coordinate pointers");
     if (a->epilogue == TC_EPI_GRU_ZR && (a->n_pad != 128 || (!a->bias2 && !a->residual) || !a->out2)) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: GRU zr epilogue needs n_pad=128, bias2, out2");
     if (a->epilogue == TC_EPI_GRU_Q && (a->n_pad != 64 || !a->z)) return fail(PVRAFT_ERR_BAD_ARG, "tc_linear: GRU q epilogue needs n_pad=64 and z");
     const long long M = (long long)a->B * a->N;
@@ -720,7 +725,7 @@ extern "C" int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream
     p.src_min = a->in_min;
     p.gn_kb = a->in_stats ? a->in_channels[0] / kTcKB : 0;
     p.tail = a->tail;
-    p.w3 = a->w3; p.b3 = a->b3; p.coords1 = a->coords1; p.coords2 = a->coords2; p.coords2_out = a->coords2_out; p.flow_out = a->flow_out;
+    p.w3 = a->w3; p.b3 = a->b3; p.coords1 = a->coords1; p.coords2 = a->coords2; p.coords2_out = a->coords2_out; p.flow_out = a->flow_out; p.flow_user = a->flow_user; p.row_map = a->row_map;
     p.out_ld = a->tail ? a->cout + 3 : a->cout;
     if ((rc = tc_make_map(&mw_hi, a->w_hi, a->n_pad, K, K, a->n_pad)) || (rc = tc_make_map(&mw_lo, a->w_lo, a->n_pad, K, K, a->n_pad))) return rc;
     CUtensorMap ma[3], mmin;

@@ -195,6 +195,22 @@ def derived(tensors, tag, fn):
     return value
 
 
+def morton_order(points):
+    """[B,N,3] -> [B,N] int64 permutation that sorts every cloud along a 30-bit Morton (Z-order) curve: neighbouring points
+    get neighbouring rows, so the 32 neighbour rows a SetConv gathers for consecutive points overlap in L1/L2."""
+    lo, hi = points.amin(1, keepdim=True), points.amax(1, keepdim=True)
+    q = ((points - lo) / (hi - lo).clamp_min(1e-12) * 1023.0).long().clamp_(0, 1023)
+
+    def spread(v):   # 10 bits -> every third bit
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        return (v | (v << 2)) & 0x09249249
+
+    code = spread(q[..., 0]) | (spread(q[..., 1]) << 1) | (spread(q[..., 2]) << 2)
+    return torch.sort(code, dim=1, stable=True).indices
+
+
 def tc_supported(n_points, *channels):
     """The tcgen05 layer needs 128-point tiles that do not straddle samples and 32-channel k-blocks."""
     return n_points % 128 == 0 and all(c % 32 == 0 for c in channels)
@@ -203,7 +219,7 @@ def tc_supported(n_points, *channels):
 def tc_linear(sources, w, bias=None, *, in_min=None, in_stats=None, in_gamma=None, in_beta=None, in_count=0.0,
               in_act=ACT_NONE, in_slope=0.0, out_act=ACT_NONE, residual=None, out=None, out_stats=None, epilogue=TC_PLAIN,
               bias2=None, out2=None, h=None, z=None, cout=None, tail=None, w3=None, b3=None, coords1=None, coords2=None,
-              coords2_out=None, flow_out=None):
+              coords2_out=None, flow_out=None, flow_user=None, row_map=None):
     """Fused layer on the tcgen05 tensor cores.  sources: list of [B,N,C_i] tensors concatenated along K (the
     GroupNorm prologue applies to sources[0]); w = (hi, lo, n_pad, rows) from tc_weights(); tail [B,N,3] fills the
     output columns cout..cout+2."""
@@ -225,6 +241,7 @@ def tc_linear(sources, w, bias=None, *, in_min=None, in_stats=None, in_gamma=Non
     a.tail = _p(tail)
     a.w3, a.b3, a.coords1, a.coords2 = _p(w3), _p(b3), _p(coords1), _p(coords2)
     a.coords2_out, a.flow_out = _p(coords2_out), _p(flow_out)
+    a.flow_user, a.row_map = _p(flow_user), _p(row_map, torch.int32)
     _count(lib().pvraft_tc_linear_fwd(C.byref(a), _stream()), 'tc_linear')
     return out
 

@@ -33,6 +33,10 @@ class _RaftBase(nn.Module):
     # copied into the graph's static buffers, outputs are returned as copies.  Parameters are read at capture time through
     # their device pointers, so in-place weight updates are seen by replays; replaced weight tensors need `reset_graphs()`.
     use_cuda_graph = os.environ.get('PVRAFT_CUDA_GRAPH', '0') == '1'
+    # Morton-order the first cloud internally (see _encode).  Off by default: the edge kernel gains 18 % (101 -> 83 us) but the
+    # torch-side Morton sort + gathers cost more than that at B = 8 (21.34 vs 20.95 ms per forward); the permutation should
+    # come for free from the kNN grid sort.
+    sort_points = os.environ.get('PVRAFT_SORT_POINTS', '0') == '1'
 
     def reset_graphs(self):
         self.__dict__.pop('_graphs', None)
@@ -74,6 +78,15 @@ class _RaftBase(nn.Module):
             raise ValueError('expected p = [xyz1 [B,N,3], xyz2 [B,N,3]]')
         xyz1 = xyz1.detach().contiguous().float()
         xyz2 = xyz2.detach().contiguous().float()
+        # Spatial reordering of the first cloud (every op is per point or per neighbourhood, so the point order carries no
+        # meaning): along a Morton curve the 32 neighbour rows that the SetConv edge kernel gathers for consecutive points
+        # overlap in L1/L2 (edge kernel 101 -> 83 us).  The flows are written back in the caller's order (`row_map`).
+        self._row_map = None
+        if self.sort_points and ops.tc_supported(xyz1.shape[1]):
+            perm = ops.morton_order(xyz1)
+            xyz1 = torch.gather(xyz1, 1, perm.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+            offs = (torch.arange(xyz1.shape[0], device=xyz1.device) * xyz1.shape[1]).view(-1, 1)
+            self._row_map = (perm + offs).to(torch.int32).reshape(-1).contiguous()   # row of permuted point r in the input order
         # both clouds go through the shared feature encoder as one batch of 2B samples (RAFTSceneFlow.py:25-26: every op is
         # per sample): half the launches, and 2B*N/128 tiles fill the 148 SMs more evenly
         b = xyz1.shape[0]
@@ -117,12 +130,22 @@ class _RaftBase(nn.Module):
 
                 _, keep = self.corr_block.feature_point_major(coords2, motion_args=attach)   # :42 + update.py:83
             new_flow = torch.empty_like(xyz1)
+            user_flow = torch.empty_like(xyz1) if (keep_all and self._row_map is not None) else None   # caller's point order
             net, _ = self.update_block.forward_pm(net, inp, motion, graph_context, gru_pre=self._gru_pre, coords1=xyz1, coords2=coords2,
-                                                  coords2_out=coords2, flow_out=new_flow)   # :44-46
+                                                  coords2_out=coords2, flow_out=new_flow, flow_user=user_flow,
+                                                  row_map=self._row_map if user_flow is not None else None)   # :44-46
             flow = new_flow
             if keep_all:
-                preds.append(flow)
+                preds.append(flow if user_flow is None else user_flow)
         return flow, preds
+
+    def _to_input_order(self, x):
+        """[B,N,C] in the internal (Morton) point order -> the caller's order."""
+        if self._row_map is None:
+            return x
+        out = torch.empty_like(x)
+        out.view(-1, x.shape[-1])[self._row_map.long()] = x.reshape(-1, x.shape[-1])
+        return out
 
 
 class RSF(_RaftBase):
@@ -157,4 +180,4 @@ class RSF_refine(_RaftBase):
     def _forward_impl(self, p, num_iters=12):
         xyz1, _, graph, graph_context, net, inp = self._encode(p)
         flow, _ = self._iterate(xyz1, graph_context, net, inp, num_iters, keep_all=False)
-        return self.refine_block(flow, graph)                            # RAFTSceneFlowRefine.py:46
+        return self._to_input_order(self.refine_block(flow, graph))      # RAFTSceneFlowRefine.py:46

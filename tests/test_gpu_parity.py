@@ -482,3 +482,25 @@ def test_gru_context_terms_match_full_gemm(dev):
         full = gru.forward_pm(net, inp, motion)
         fast = gru.forward_pm(net, inp, motion, pre=gru.context_terms(inp))
     assert rel_err(fast.cpu(), full.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize('refine', [False, True])
+def test_internal_point_reordering_is_invisible(dev, refine):
+    """RSF / RSF_refine Morton-order the first cloud internally: the returned flows are in the caller's order and agree with
+    the unsorted run (the only differences are summation orders of GroupNorm statistics)."""
+    from pvraft_b200 import RSF, RSF_refine
+    args = types.SimpleNamespace(corr_levels=3, base_scales=0.25, truncate_k=128)
+    torch.manual_seed(1)
+    m = (RSF_refine if refine else RSF)(args).to(dev).eval()
+    pc1, pc2 = [t.to(dev) for t in O.synthetic_clouds(2, 1024, seed=9)]
+    with torch.no_grad():
+        m.sort_points = False
+        plain = m([pc1, pc2], 3)
+        m.sort_points = True
+        sorted_ = m([pc1, pc2], 3)
+    assert m._row_map is not None
+    plain = [plain] if torch.is_tensor(plain) else plain
+    sorted_ = [sorted_] if torch.is_tensor(sorted_) else sorted_
+    assert len(plain) == len(sorted_)
+    for a, b in zip(plain, sorted_):
+        assert a.shape == b.shape and float((a - b).abs().mean()) < 2e-3 * float(a.abs().mean())   # free-running tolerance
