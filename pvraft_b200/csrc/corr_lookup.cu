@@ -45,6 +45,7 @@ struct LookupParams {
     float r[4];          // cell edge per level
     float inv_r[4];      // exact reciprocal when r is a power of two
     int warps;           // warps per block actually carved in shared memory
+    int chunk;           // points per dynamic work claim
 };
 
 template <bool POW2>
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
     __syncthreads();
 
     // Work distribution.  With a moment buffer (zeroed by the caller) and at least one CTA per sample, the CTAs of a sample
-    // share its points dynamically: warps claim chunks of 8 consecutive points from a counter kept in the unused 16th moment
+    // share its points dynamically: warps claim chunks of 4 consecutive points from a counter kept in the unused 16th moment
     // slot (the per-point cost varies ~2x with the local density, and a cloud's points are usually stored region by region,
     // so equal contiguous shares left ~20 % of the SM time idle).  Otherwise: equal contiguous shares of B*N.
     const bool dyn = p.moments != nullptr && (int)gridDim.x >= p.B;
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
     const float rc = L == 1 ? p.r[0] : L == 2 ? p.r[1] : L == 3 ? p.r[2] : p.r[3];               // coarsest level
     const float inv_rc = L == 1 ? p.inv_r[0] : L == 2 ? p.inv_r[1] : L == 3 ? p.inv_r[2] : p.inv_r[3];
     unsigned phase0 = 0, phase1 = 0;
-    constexpr int kChunk = 8;
+    const int kChunk = p.chunk;
 
     long long seg = pt_begin;
     while (seg < pt_end) {
@@ -554,6 +555,8 @@ static int launch_lookup(LookupParams& p, cudaStream_t st) {
     if (warps > kLookupThreads / 32) warps = kLookupThreads / 32;
     if (warps < 1) return fail(PVRAFT_ERR_SMEM, "corr_lookup: K=%d does not fit shared memory", K);
     p.warps = warps;
+    p.chunk = 4;   // in-situ sweep at B=8, N=8192: 1 -> 0.137 ms, 2 -> 0.129, 3 -> 0.127, 4 -> 0.127, 8 -> 0.129, 16 -> 0.154, 32 -> 0.161
+    if (const char* e = getenv("PVRAFT_LOOKUP_CHUNK")) { const int v = atoi(e); if (v >= 1 && v <= 64) p.chunk = v; }
     const size_t rcp = (size_t)(K + 1) * sizeof(double) + 8;
     const size_t smem = (smem_tab ? tab : 0) + warps * per_warp + rcp;
     const long long total = (long long)p.B * p.N;
