@@ -353,6 +353,12 @@ PVRAFT_API int64_t pvraft_knn_workspace_bytes(int B, int N);
 PVRAFT_API int pvraft_knn_fwd(const float* xyz, const float* query, int B, int N, int S, int k, int mode, int32_t* idx,
                    float* rel, void* workspace, void* stream);
 
+/* A spatially coherent order of every cloud: perm[b, r] = index of the point that comes r-th along a Morton (Z-order) curve
+ * over the cells of the kNN grid.  No counterpart in the reference (point order carries no meaning in model/*.py); the
+ * RAFT driver uses it to make the SetConv gathers of consecutive points overlap in L1/L2.  64 <= N <= 16384;
+ * workspace: pvraft_knn_workspace_bytes(B, N) bytes. */
+PVRAFT_API int pvraft_point_order_fwd(const float* xyz, int B, int N, int32_t* perm, void* workspace, void* stream);
+
 /* sizeof() of the argument structs as compiled into the library (0 = linear, 1 = corrfeat, 2 = gru,
  * 3 = flowout, 4 = tc_linear; -1 otherwise): lets a foreign-language binding verify its struct layout at load time. */
 PVRAFT_API int pvraft_sizeof(int which);

@@ -80,6 +80,7 @@ _SIGNATURES = {
                                     C.c_int, VP, VP]),
     'pvraft_corr_feature_fwd': (C.c_int, [C.POINTER(CorrFeatArgs), VP]),
     'pvraft_knn_branch_fwd': (C.c_int, [C.POINTER(KnnBranchArgs), VP]),
+    'pvraft_point_order_fwd': (C.c_int, [VP, C.c_int, C.c_int, VP, VP, VP]),
     'pvraft_gru_fwd': (C.c_int, [C.POINTER(GruArgs), VP]),
     'pvraft_setconv_edge_fwd': (C.c_int, [VP, VP, VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, VP, VP, VP, VP]),
     'pvraft_flow_out_fwd': (C.c_int, [C.POINTER(FlowOutArgs), VP]),

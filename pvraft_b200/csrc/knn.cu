@@ -137,7 +137,9 @@ __device__ __forceinline__ int cell_coord(float v, float gmin, float inv_h, int 
     return c < 0 ? 0 : (c >= G ? G - 1 : c);
 }
 
-__global__ void __launch_bounds__(1024) k_grid_sort(const float* __restrict__ xyz, int N, int NP /*pow2 >= N*/, float occ, GridParams* __restrict__ params,
+// `morton` != 0: the sort key is the Morton (Z-order) interleave of the cell coordinates instead of the linear cell id, and only
+// `ids` (the permutation) is of interest to the caller: a spatially coherent point order (pvraft_point_order_fwd).
+__global__ void __launch_bounds__(1024) k_grid_sort(const float* __restrict__ xyz, int N, int NP /*pow2 >= N*/, float occ, int morton, GridParams* __restrict__ params,
                                                      float4* __restrict__ sorted, int32_t* __restrict__ ids, unsigned* __restrict__ keys) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* s = reinterpret_cast<unsigned long long*>(smem_raw);   // (cell id << 32) | point id
@@ -198,7 +200,13 @@ __global__ void __launch_bounds__(1024) k_grid_sort(const float* __restrict__ xy
             const int cx = cell_coord(__ldg(X + (size_t)i * 3), gp.gmin[0], gp.inv_h[0], gp.G[0]);
             const int cy = cell_coord(__ldg(X + (size_t)i * 3 + 1), gp.gmin[1], gp.inv_h[1], gp.G[1]);
             const int cz = cell_coord(__ldg(X + (size_t)i * 3 + 2), gp.gmin[2], gp.inv_h[2], gp.G[2]);
-            const unsigned key = (unsigned)((cz * gp.G[1] + cy) * gp.G[0] + cx);
+            unsigned key = (unsigned)((cz * gp.G[1] + cy) * gp.G[0] + cx);
+            if (morton) {   // cell coordinates are < 64: spread 6 bits each over every third bit
+                key = 0u;
+#pragma unroll
+                for (int bit = 0; bit < 6; ++bit)
+                    key |= (((unsigned)cx >> bit) & 1u) << (3 * bit) | (((unsigned)cy >> bit) & 1u) << (3 * bit + 1) | (((unsigned)cz >> bit) & 1u) << (3 * bit + 2);
+            }
             e = ((unsigned long long)key << 32) | (unsigned)i;
         }
         s[i] = e;
@@ -341,7 +349,7 @@ extern "C" int pvraft_knn_fwd(const float* xyz, const float* query, int B, int N
         if ((rc = opt_in_smem(k_grid_sort, smem))) return rc;
         float occ = kCellOcc;
         if (const char* e = getenv("PVRAFT_KNN_OCC")) { const float v = (float)atof(e); if (v > 0.f) occ = v; }
-        k_grid_sort<<<B, 1024, smem, st>>>(xyz, N, NP, occ, params, sorted, ids, keys);
+        k_grid_sort<<<B, 1024, smem, st>>>(xyz, N, NP, occ, 0, params, sorted, ids, keys);
         if ((rc = check_launch("knn grid sort"))) return rc;
         k_grid_cells<<<dim3((kMaxCells + 1 + 255) / 256, B), 256, 0, st>>>(keys, N, cell_start);
         if ((rc = check_launch("knn grid cells"))) return rc;
@@ -350,4 +358,26 @@ extern "C" int pvraft_knn_fwd(const float* xyz, const float* query, int B, int N
     }
     k_knn<<<grid, kKnnThreads, 0, st>>>(xyz, query, N, S, k, mode, idx, rel);
     return check_launch("knn");
+}
+
+extern "C" int pvraft_point_order_fwd(const float* xyz, int B, int N, int32_t* perm, void* workspace, void* stream) {
+    if (!xyz || !perm || !workspace) return fail(PVRAFT_ERR_BAD_ARG, "point_order: null pointer");
+    if (B <= 0 || N < 64 || N > kSortMaxN || B > 65535) return fail(PVRAFT_ERR_UNSUPPORTED, "point_order: B=%d, N=%d (64 <= N <= %d)", B, N, kSortMaxN);
+    cudaStream_t st = (cudaStream_t)stream;
+    int NP = 1;
+    while (NP < N) NP <<= 1;
+    // same workspace layout as pvraft_knn_fwd; the permutation is the `ids` array of the sort
+    float4* sorted = reinterpret_cast<float4*>(workspace);
+    int32_t* ids = reinterpret_cast<int32_t*>(sorted + (size_t)B * N);
+    unsigned* keys = reinterpret_cast<unsigned*>(ids + (size_t)B * N);
+    int32_t* cell_start = reinterpret_cast<int32_t*>(keys + (size_t)B * N);
+    GridParams* params = reinterpret_cast<GridParams*>((reinterpret_cast<uintptr_t>(cell_start + (size_t)B * (kMaxCells + 1)) + 15) & ~(uintptr_t)15);
+    const size_t smem = (size_t)NP * sizeof(unsigned long long);
+    int rc;
+    if ((rc = opt_in_smem(k_grid_sort, smem))) return rc;
+    k_grid_sort<<<B, 1024, smem, st>>>(xyz, N, NP, kCellOcc, 1, params, sorted, ids, keys);
+    if ((rc = check_launch("point order sort"))) return rc;
+    const cudaError_t e = cudaMemcpyAsync(perm, ids, (size_t)B * N * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return fail((int)e, "point_order: copy failed: %s", cudaGetErrorString(e));
+    return 0;
 }

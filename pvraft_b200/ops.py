@@ -195,6 +195,19 @@ def derived(tensors, tag, fn):
     return value
 
 
+def point_order(points):
+    """[B,N,3] -> [B,N] int64: Morton order over the cells of the kNN grid, from the library's in-shared-memory sort (one
+    launch; the torch formulation below costs ~40 launches)."""
+    b, n, _ = points.shape
+    ws_bytes = int(lib().pvraft_knn_workspace_bytes(b, n))
+    if ws_bytes <= 0 or n < 64:
+        return morton_order(points)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=points.device)
+    perm = torch.empty(b, n, dtype=torch.int32, device=points.device)
+    _count(lib().pvraft_point_order_fwd(_p(points), b, n, _p(perm, torch.int32), _p(ws, torch.uint8), _stream()), 'point_order')
+    return perm.long()
+
+
 def morton_order(points):
     """[B,N,3] -> [B,N] int64 permutation that sorts every cloud along a 30-bit Morton (Z-order) curve: neighbouring points
     get neighbouring rows, so the 32 neighbour rows a SetConv gathers for consecutive points overlap in L1/L2."""

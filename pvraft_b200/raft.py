@@ -33,9 +33,9 @@ class _RaftBase(nn.Module):
     # copied into the graph's static buffers, outputs are returned as copies.  Parameters are read at capture time through
     # their device pointers, so in-place weight updates are seen by replays; replaced weight tensors need `reset_graphs()`.
     use_cuda_graph = os.environ.get('PVRAFT_CUDA_GRAPH', '0') == '1'
-    # Morton-order the first cloud internally (see _encode).  Off by default: the edge kernel gains 18 % (101 -> 83 us) but the
-    # torch-side Morton sort + gathers cost more than that at B = 8 (21.34 vs 20.95 ms per forward); the permutation should
-    # come for free from the kNN grid sort.
+    # Morton-order the first cloud internally (see _encode).  Off by default: in isolation the edge kernel gains 18 %
+    # (101 -> 83 us), but per forward it is a wash at B = 8 (20.87 vs 20.88 ms with the order from the library's grid sort,
+    # 21.34 with a torch-side sort).
     sort_points = os.environ.get('PVRAFT_SORT_POINTS', '0') == '1'
 
     def reset_graphs(self):
@@ -83,7 +83,7 @@ class _RaftBase(nn.Module):
         # overlap in L1/L2 (edge kernel 101 -> 83 us).  The flows are written back in the caller's order (`row_map`).
         self._row_map = None
         if self.sort_points and ops.tc_supported(xyz1.shape[1]):
-            perm = ops.morton_order(xyz1)
+            perm = ops.point_order(xyz1)
             xyz1 = torch.gather(xyz1, 1, perm.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
             offs = (torch.arange(xyz1.shape[0], device=xyz1.device) * xyz1.shape[1]).view(-1, 1)
             self._row_map = (perm + offs).to(torch.int32).reshape(-1).contiguous()   # row of permuted point r in the input order
