@@ -10,7 +10,7 @@ import torch.nn as nn
 
 from . import _lib, ops
 from .gconv import SetConv
-from .ops import ACT_LRELU, IN_GN, IN_GN_MINMAX
+
 
 
 def _w(p):

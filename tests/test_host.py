@@ -180,3 +180,15 @@ def test_derived_cache_follows_parameter_versions():
     assert ops.derived((w,), 'sum', make) == 8.0 and len(calls) == 2
     w.data = torch.full((4,), 3.0)                      # storage swap (e.g. module.to(device)) -> re-derived
     assert ops.derived((w,), 'sum', make) == 12.0 and len(calls) == 3
+
+
+def test_morton_order_is_a_spatially_coherent_permutation():
+    from pvraft_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    pts = torch.rand(2, 4096, 3, generator=g) * torch.tensor([20.0, 10.0, 2.0])
+    perm = ops.morton_order(pts)
+    assert perm.shape == (2, 4096) and torch.equal(perm.sort(1).values, torch.arange(4096).expand(2, -1))
+    ordered = torch.gather(pts, 1, perm.unsqueeze(-1).expand(-1, -1, 3))
+    step_sorted = (ordered[:, 1:] - ordered[:, :-1]).norm(dim=-1).mean()
+    step_input = (pts[:, 1:] - pts[:, :-1]).norm(dim=-1).mean()
+    assert step_sorted < 0.25 * step_input          # consecutive rows are spatial neighbours
