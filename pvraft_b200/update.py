@@ -12,7 +12,6 @@ from . import _lib, ops
 from .gconv import SetConv
 
 
-
 def _w(p):
     return p.detach()
 
