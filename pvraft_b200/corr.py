@@ -21,6 +21,15 @@ def _w(p):
     return p.detach()
 
 
+def fold_corr_motion(w_cc, b_cc, w_out, b_out, w_kout, b_kout):
+    """conv_corr(out_conv.3(a) + knn_out(k)) = W_cc [W_out | W_kout] [a, k] + (W_cc (b_out + b_kout) + b_cc)
+    (model/corr.py:45 then model/update.py:16): the folded [64,192] weight and [64] bias, float64 products rounded once."""
+    wc = w_cc.detach().reshape(64, 64).double()
+    wcat = torch.cat([w_out.detach().reshape(64, 128), w_kout.detach().reshape(64, 64)], 1).double()
+    return ((wc @ wcat).float().contiguous(),
+            (wc @ (b_out.detach().double() + b_kout.detach().double()) + b_cc.detach().double()).float().contiguous())
+
+
 class CorrBlock(nn.Module):
     def __init__(self, num_levels=3, base_scale=0.25, resolution=3, truncate_k=128, knn=32):
         super().__init__()
@@ -181,14 +190,8 @@ class CorrBlock(nn.Module):
         else:
             # the loop only consumes relu(conv_corr(corr)) (update.py:16), and corr is linear in [a1, kfeat]: fold conv_corr
             # into the weights, W_cc [W_out | W_kout] with bias W_cc (b_out + b_kout) + b_cc (float64 products, rounded once)
-            def fold(w_cc, b_cc, w_out, b_out, w_kout, b_kout):
-                wc = w_cc.detach().reshape(64, 64).double()
-                wcat = torch.cat([w_out.detach().reshape(64, 128), w_kout.detach().reshape(64, 64)], 1).double()
-                return ((wc @ wcat).float().contiguous(),
-                        (wc @ (b_out.detach().double() + b_kout.detach().double()) + b_cc.detach().double()).float().contiguous())
-
             w_eff, b_eff = ops.derived((me.conv_corr.weight, me.conv_corr.bias, oc[3].weight, oc[3].bias, self.knn_out.weight,
-                                        self.knn_out.bias), 'corr_cc', fold)
+                                        self.knn_out.bias), 'corr_cc', fold_corr_motion)
             corr = None
             cc = ops.tc_linear([y1, kfeat], ops.tc_weights(w_eff), b_eff, out_act=ACT_RELU, **gn)
         motion = ops.tc_linear([cc, cflow], ops.tc_weights(me.conv.weight), _w(me.conv.bias), out_act=ACT_RELU, tail=flow)

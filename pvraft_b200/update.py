@@ -16,6 +16,15 @@ def _w(p):
     return p.detach()
 
 
+def fold_flow_head(w_o0, w_c1, b_c1, b_o0):
+    """out_conv.0([s, conv1(x)]) = [W_a | W_b W_c1] [s, x] + (W_b b_c1 + b_o0) with out_conv.0.weight = [W_a | W_b]
+    (model/update.py:68-71): the folded [64,128] weight and [64] bias, products in float64 rounded once to fp32."""
+    wo = w_o0.detach().reshape(64, 128).double()
+    wc, bc = w_c1.detach().reshape(64, 64).double(), b_c1.detach().double()
+    w = torch.cat([wo[:, :64], wo[:, 64:] @ wc], 1).float().contiguous()
+    return w, (wo[:, 64:] @ bc + b_o0.detach().double()).float().contiguous()
+
+
 class MotionEncoder(nn.Module):
     def __init__(self):
         super().__init__()
@@ -140,13 +149,7 @@ class FlowHead(nn.Module):
             # conv1 is folded into the second half of its weight: W [a3 | W_b W_c1] with bias W_b b_c1 + b_o0 (products in
             # float64, rounded once).  Prologue: a3 = lrelu(GN3(z3)); epilogue: ReLU, out_conv.2 and the RAFT update
             # (update.py:72, RAFTSceneFlow.py:45-46).
-            def fold(w_o0, w_c1, b_c1, b_o0):
-                wo = w_o0.detach().reshape(64, 128).double()
-                wc, bc = w_c1.detach().reshape(64, 64).double(), b_c1.detach().double()
-                w = torch.cat([wo[:, :64], wo[:, 64:] @ wc], 1).float().contiguous()
-                return w, (wo[:, 64:] @ bc + b_o0.detach().double()).float().contiguous()
-
-            w_eff, b_eff = ops.derived((oc[0].weight, self.conv1.weight, self.conv1.bias, oc[0].bias), 'flowhead', fold)
+            w_eff, b_eff = ops.derived((oc[0].weight, self.conv1.weight, self.conv1.bias, oc[0].bias), 'flowhead', fold_flow_head)
             ops.tc_linear([d.z, net], ops.tc_weights(w_eff), b_eff, in_stats=d.stats, in_gamma=d.gamma, in_beta=d.beta,
                           in_count=d.count, in_act=ops.ACT_LRELU, in_slope=0.1, epilogue=ops.TC_FLOW, out=delta, cout=64,
                           w3=_w(oc[2].weight), b3=_w(oc[2].bias), coords1=coords1, coords2=coords2, coords2_out=coords2_out,

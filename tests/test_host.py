@@ -192,3 +192,26 @@ def test_morton_order_is_a_spatially_coherent_permutation():
     step_sorted = (ordered[:, 1:] - ordered[:, :-1]).norm(dim=-1).mean()
     step_input = (pts[:, 1:] - pts[:, :-1]).norm(dim=-1).mean()
     assert step_sorted < 0.25 * step_input          # consecutive rows are spatial neighbours
+
+
+def test_weight_folds_equal_the_unfused_layers():
+    """The two algebraic folds of the RAFT loop, against the unfused layer sequences in float64."""
+    from pvraft_b200.corr import fold_corr_motion
+    from pvraft_b200.update import fold_flow_head
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s: torch.randn(*s, generator=g)
+    # flow head: out_conv.0(cat([s, conv1(x)]))
+    w_o0, b_o0, w_c1, b_c1 = r(64, 128, 1), r(64), r(64, 64, 1), r(64)
+    s_, x = r(5, 64).double(), r(5, 64).double()
+    want = torch.cat([s_, x @ w_c1[..., 0].double().T + b_c1.double()], 1) @ w_o0[..., 0].double().T + b_o0.double()
+    w, b = fold_flow_head(w_o0, w_c1, b_c1, b_o0)
+    got = torch.cat([s_, x], 1) @ w.double().T + b.double()
+    assert float((got - want).abs().max() / want.abs().max()) < 1e-6
+    # feature head + conv_corr: conv_corr(out_conv.3(a) + knn_out(k))
+    w_cc, b_cc, w_out, b_out, w_kout, b_kout = r(64, 64, 1), r(64), r(64, 128, 1), r(64), r(64, 64, 1), r(64)
+    a, k = r(5, 128).double(), r(5, 64).double()
+    corr = a @ w_out[..., 0].double().T + b_out.double() + k @ w_kout[..., 0].double().T + b_kout.double()
+    want = corr @ w_cc[..., 0].double().T + b_cc.double()
+    w, b = fold_corr_motion(w_cc, b_cc, w_out, b_out, w_kout, b_kout)
+    got = torch.cat([a, k], 1) @ w.double().T + b.double()
+    assert float((got - want).abs().max() / want.abs().max()) < 1e-6
