@@ -60,12 +60,25 @@ class CorrBlock(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     @staticmethod
+    def calculate_corr_pm(fmap1_pm, fmap2_pm):
+        """Point-major [B,N,C] feature maps -> corr [B,N,N] = <f1_i, f2_j> / sqrt(C) on the tcgen05 GEMM (3xTF32, fp32-accurate).
+        The kernel works on 128-point tiles: a ragged N is zero-padded to the next multiple of 128 and the result cropped
+        (no library GEMM on any path)."""
+        b, n, c = fmap1_pm.shape
+        if c % 32 != 0:
+            raise NotImplementedError(f'calculate_corr: {c} feature channels (the tcgen05 GEMM needs a multiple of 32; the model has 128)')
+        pad = (-n) % 128
+        if pad == 0:
+            return ops.corr_matmul(fmap1_pm, fmap2_pm)
+        f1 = torch.nn.functional.pad(fmap1_pm, (0, 0, 0, pad)).contiguous()
+        f2 = torch.nn.functional.pad(fmap2_pm, (0, 0, 0, pad)).contiguous()
+        return ops.corr_matmul(f1, f2)[:, :n, :n].contiguous()
+
+    @staticmethod
     def calculate_corr(fmap1, fmap2):
-        """model/corr.py:95-100, kept for API parity (a plain library GEMM).  init_module uses the
-        tcgen05 kernel (ops.corr_matmul) whenever N % 128 == 0 and C % 32 == 0."""
-        dim = fmap1.shape[1]
-        corr = torch.matmul(fmap1.transpose(1, 2), fmap2)
-        return corr / torch.sqrt(torch.tensor(dim).float())
+        """model/corr.py:95-100 with the reference's channel-major [B,C,N] arguments."""
+        return CorrBlock.calculate_corr_pm(ops.transpose(fmap1.detach().contiguous().float()),
+                                           ops.transpose(fmap2.detach().contiguous().float()))
 
     def init_module(self, fmap1, fmap2, xyz2):
         """model/corr.py:31-42: build the truncated correlation state for one forward pass
@@ -78,11 +91,7 @@ class CorrBlock(nn.Module):
         b, n_p, _ = xyz2.shape
         if n_p < self.truncate_k:
             raise ValueError(f'truncate_k={self.truncate_k} exceeds the number of points {n_p}')
-        c = fmap1_pm.shape[-1]
-        if n_p % 128 == 0 and c % 32 == 0:
-            corr = ops.corr_matmul(fmap1_pm, fmap2_pm)          # tcgen05, 3xTF32 (fp32-accurate)
-        else:                                                   # odd sizes: the library GEMM of calculate_corr
-            corr = self.calculate_corr(fmap1_pm.transpose(1, 2), fmap2_pm.transpose(1, 2)).contiguous()
+        corr = self.calculate_corr_pm(fmap1_pm.contiguous(), fmap2_pm.contiguous())   # tcgen05, 3xTF32 (fp32-accurate)
         val, idx = ops.corr_topk(corr, self.truncate_k)
         self.corr_val, self.corr_idx = ops.corr_reorder(val, idx)
         self._xyz2 = xyz2.detach().contiguous().float()

@@ -160,6 +160,10 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
     if (active_warp && lane == 0) { mbar_init(s_bar, 1); mbar_init(s_bar + 1, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+    // Launched with PDL: only the set-up above overlaps the previous kernel's tail.  Everything below reads what earlier
+    // kernels of the stream wrote -- the zeroed per-sample work counter (griddepcontrol.wait is what makes the
+    // predecessor's stores visible), the query coordinates -- or writes buffers they may still read.
+    pdl_wait();
 
     // Work distribution.  With a moment buffer (zeroed by the caller) and at least one CTA per sample, the CTAs of a sample
     // share its points dynamically: warps claim chunks of 4 consecutive points from a counter kept in the unused 16th moment
@@ -211,10 +215,6 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
             for (int i = threadIdx.x; i < p.N * 3; i += blockDim.x) s_tab[i] = __ldg(tab_g + i);
         }
         __syncthreads();
-        // Launched with PDL: everything above (reciprocal table, barriers, the sample's xyz table, the first candidate row)
-        // reads data that no kernel of the loop writes and may overlap the previous kernel's tail; the query coordinates
-        // below are written by the flow head, and the outputs may reuse memory the previous kernel still reads.
-        pdl_wait();
         double mom[14];
 #pragma unroll
         for (int i = 0; i < 14; ++i) mom[i] = 0.0;

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kTopkThreads) k_corr_topk_vec(const float* __r
     uint4* s_key = reinterpret_cast<uint4*>(smem_raw);   // [8 * 256]
     __shared__ int s_hist[2048];
     __shared__ int s_wsum[kTopkThreads / 32];
-    __shared__ unsigned s_scan[kTopkThreads / 32][6];
+    __shared__ unsigned s_scan[kTopkThreads / 32][7];
     __shared__ unsigned s_prefix;
     __shared__ int s_need;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -204,37 +204,39 @@ __global__ void __launch_bounds__(kTopkThreads) k_corr_topk_vec(const float* __r
     const unsigned T = prefix;   // exact K-th largest key
     const int need_eq = need;    // how many keys == T belong to the top-K (lowest columns first)
     // ---- ordered compaction: chunk j = columns [1024 j, 1024 j + 1024), inside a chunk thread order = column order ----
-    unsigned cnt[6] = {0u, 0u, 0u, 0u, 0u, 0u};   // words 0-2: keys > T per chunk (11-bit fields), words 3-5: keys == T
+    // words 0-2: keys > T per chunk in 11-bit fields (at most K - 1 <= 1023 keys exceed T, so no field overflows);
+    // words 3-6: keys == T per chunk in 16-bit fields (a whole 1024-key chunk may tie with T: 11 bits at shift 22 would wrap)
+    unsigned cnt[7] = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const uint4 kk = s_key[j * kTopkThreads + tid];
         const unsigned g = (kk.x > T) + (kk.y > T) + (kk.z > T) + (kk.w > T);
         const unsigned q = (kk.x == T) + (kk.y == T) + (kk.z == T) + (kk.w == T);
         cnt[j / 3] += g << (11 * (j % 3));
-        cnt[3 + j / 3] += q << (11 * (j % 3));
+        cnt[3 + j / 2] += q << (16 * (j % 2));
     }
-    unsigned inc[6];
+    unsigned inc[7];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) inc[i] = cnt[i];
+    for (int i = 0; i < 7; ++i) inc[i] = cnt[i];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
+        for (int i = 0; i < 7; ++i) {
             const unsigned a = __shfl_up_sync(kFull, inc[i], o);
             if (lane >= o) inc[i] += a;
         }
     }
     if (lane == 31) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) s_scan[w][i] = inc[i];
+        for (int i = 0; i < 7; ++i) s_scan[w][i] = inc[i];
     }
     __syncthreads();
-    unsigned tot[6] = {0u, 0u, 0u, 0u, 0u, 0u}, before[6];
+    unsigned tot[7] = {0u, 0u, 0u, 0u, 0u, 0u, 0u}, before[7];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) before[i] = inc[i] - cnt[i];   // exclusive within the warp
+    for (int i = 0; i < 7; ++i) before[i] = inc[i] - cnt[i];   // exclusive within the warp
     for (int ww = 0; ww < kTopkThreads / 32; ++ww) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
+        for (int i = 0; i < 7; ++i) {
             const unsigned a = s_scan[ww][i];
             tot[i] += a;
             if (ww < w) before[i] += a;
@@ -247,12 +249,12 @@ __global__ void __launch_bounds__(kTopkThreads) k_corr_topk_vec(const float* __r
     int base_gt = 0, base_eq = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int sh = 11 * (j % 3);
+        const int sh = 11 * (j % 3), sq = 16 * (j % 2);
         int gt_before = base_gt + (int)((before[j / 3] >> sh) & 0x7FFu);
-        int eq_before = base_eq + (int)((before[3 + j / 3] >> sh) & 0x7FFu);
+        int eq_before = base_eq + (int)((before[3 + j / 2] >> sq) & 0xFFFFu);
         base_gt += (int)((tot[j / 3] >> sh) & 0x7FFu);
-        base_eq += (int)((tot[3 + j / 3] >> sh) & 0x7FFu);
-        const unsigned mine = ((cnt[j / 3] >> sh) | (cnt[3 + j / 3] >> sh)) & 0x7FFu;   // any key >= T in this group?
+        base_eq += (int)((tot[3 + j / 2] >> sq) & 0xFFFFu);
+        const unsigned mine = ((cnt[j / 3] >> sh) & 0x7FFu) | ((cnt[3 + j / 2] >> sq) & 0xFFFFu);   // any key >= T in this group?
         if (mine == 0u) continue;
         const int col = (j * kTopkThreads + tid) * 4;
         const uint4 kk = s_key[j * kTopkThreads + tid];

@@ -5,6 +5,7 @@ hot path happens inside libpvraft_b200.so.  All wrappers require contiguous CUDA
 on anything else -- there is deliberately no CPU / eager fallback.
 """
 import ctypes as C
+import threading
 import weakref
 
 import torch
@@ -16,6 +17,9 @@ launch_count = 0   # C-ABI calls that launch a kernel (bench.py reports it as gp
 
 
 def _stream():
+    """The current stream of the CURRENT device: the library launches on the current device, so every operand has to live
+    there (`_p` checks it) -- RSF.forward enters `torch.cuda.device(input.device)` itself; callers of the inner modules on
+    a non-default GPU do the same (or `torch.cuda.set_device`), as under DDP / DataParallel."""
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -26,6 +30,9 @@ def _p(t, dtype=torch.float32):
         raise TypeError(f'expected a tensor, got {type(t)}')
     if not t.is_cuda:
         raise _lib.PvraftError('pvraft_b200 kernels need CUDA tensors (no CPU fallback exists)')
+    if t.device.index != torch.cuda.current_device():
+        raise _lib.PvraftError(f'tensor on {t.device} but the current CUDA device is {torch.cuda.current_device()}: the kernels '
+                               'launch on the current device -- wrap the call in `with torch.cuda.device(t.device):`')
     if t.dtype != dtype:
         raise TypeError(f'expected {dtype}, got {t.dtype}')
     if not t.is_contiguous():
@@ -39,7 +46,8 @@ def _count(rc, what):
     launch_count += 1
 
 
-_ARENA = None   # [buffer [n,B,8,2] f64, next free block]: zeroed accumulators handed out inside a `stats_arena` scope
+_TLS = threading.local()   # .arena = [buffer [n,B,8,2] f64, next free block]: zeroed accumulators handed out inside a
+                           # `stats_arena` scope (per thread: nn.DataParallel runs one replica per thread)
 
 
 class stats_arena:
@@ -50,22 +58,22 @@ class stats_arena:
         self.buf = [torch.zeros(blocks, b, 8, 2, dtype=torch.float64, device=device), 0]
 
     def __enter__(self):
-        global _ARENA
-        self.prev, _ARENA = _ARENA, self.buf
+        self.prev = getattr(_TLS, 'arena', None)
+        _TLS.arena = self.buf
         return self
 
     def __exit__(self, *exc):
-        global _ARENA
-        _ARENA = self.prev
+        _TLS.arena = self.prev
         return False
 
 
 def new_stats(b, device, n=1):
     """Zeroed GroupNorm accumulators: n x [B,8,2] doubles (one cudaMemset for all of them)."""
-    if _ARENA is not None:
-        buf, pos = _ARENA
+    arena = getattr(_TLS, 'arena', None)
+    if arena is not None:
+        buf, pos = arena
         if pos + n <= buf.shape[0] and buf.shape[1] == b and buf.device == torch.device(device):
-            _ARENA[1] = pos + n
+            arena[1] = pos + n
             return buf[pos:pos + n]
     return torch.zeros(n, b, 8, 2, dtype=torch.float64, device=device)
 

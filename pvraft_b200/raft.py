@@ -30,8 +30,10 @@ class _RaftBase(nn.Module):
     # CUDA-graph replay of the whole forward (encoders, correlation build, all iterations): the eager path costs ~28 us of
     # host time per launch (python + ctypes + tensor-map encodes), which bounds small batches (B <= 2: ~0.5 ms per
     # iteration).  Opt-in: `model.use_cuda_graph = True` or PVRAFT_CUDA_GRAPH=1.  One graph per (B, N, num_iters); inputs are
-    # copied into the graph's static buffers, outputs are returned as copies.  Parameters are read at capture time through
-    # their device pointers, so in-place weight updates are seen by replays; replaced weight tensors need `reset_graphs()`.
+    # copied into the graph's static buffers, outputs are returned as copies.  The kernels read DERIVED copies of the weights
+    # (tf32 hi/lo splits, folded products, bias sums, PReLU slopes known to the host) that are fixed at capture time, so a
+    # graph is only valid for the parameter values it was captured with: every entry records (version, data_ptr) of all
+    # parameters and is re-captured when any of them changed (optimizer step, load_state_dict, .to()).
     use_cuda_graph = os.environ.get('PVRAFT_CUDA_GRAPH', '0') == '1'
     # Morton-order the first cloud internally (see _encode).  Off by default: in isolation the edge kernel gains 18 %
     # (101 -> 83 us), but per forward it is a wash at B = 8 (20.87 vs 20.88 ms with the order from the library's grid sort,
@@ -46,6 +48,9 @@ class _RaftBase(nn.Module):
         graphs = self.__dict__.setdefault('_graphs', {})
         key = (tuple(xyz1.shape), xyz1.device, int(num_iters))
         entry = graphs.get(key)
+        stamp = tuple((q._version, q.data_ptr()) for q in self.parameters())
+        if entry is not None and entry[3] != stamp:
+            entry = None                                   # weights changed since the capture: stale derived constants
         if entry is None:
             static_in = [torch.empty_like(xyz1), torch.empty_like(xyz2)]
             static_in[0].copy_(xyz1)
@@ -59,8 +64,8 @@ class _RaftBase(nn.Module):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 static_out = self._forward_impl(static_in, num_iters)
-            entry = graphs[key] = (graph, static_in, static_out)
-        graph, static_in, static_out = entry
+            entry = graphs[key] = (graph, static_in, static_out, stamp)
+        graph, static_in, static_out, _ = entry
         static_in[0].copy_(xyz1)
         static_in[1].copy_(xyz2)
         graph.replay()

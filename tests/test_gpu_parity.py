@@ -185,6 +185,24 @@ def test_corr_topk_degenerate_rows(dev):
     assert torch.equal(val.cpu()[0, 1], torch.full((k,), 2.5)) and torch.equal(val.cpu()[0, 2], torch.zeros(k))
 
 
+def test_corr_topk_full_chunk_of_ties(dev):
+    """A whole 1024-column chunk equal to the threshold (duplicated / padded pc2 points give identical correlations):
+    the packed per-chunk tie counters must hold 1024 (the third 11-bit field used to wrap)."""
+    from pvraft_b200 import ops
+    m, k = 8192, 512
+    for chunk in (2, 5, 7):
+        corr = torch.zeros(1, 2, m)
+        corr[0, :, chunk * 1024:(chunk + 1) * 1024] = 1.0
+        gt_cols = torch.arange(7, m, 83)[:100]
+        gt_cols = gt_cols[(gt_cols < chunk * 1024) | (gt_cols >= (chunk + 1) * 1024)]
+        corr[0, 0, gt_cols] = 2.0
+        val, idx = ops.corr_topk(corr.to(dev), k)
+        for r, ngt in ((0, len(gt_cols)), (1, 0)):
+            want = torch.cat([gt_cols if r == 0 else gt_cols[:0], torch.arange(chunk * 1024, chunk * 1024 + k - ngt)]).sort().values
+            assert torch.equal(idx.cpu()[0, r].long(), want), (chunk, r)
+            assert torch.equal(val.cpu()[0, r], corr[0, r, want])
+
+
 @pytest.mark.parametrize('b,n', [(2, 256), (1, 1000), (1, 4096)])
 def test_knn_graph_matches_oracle(dev, b, n):
     from pvraft_b200 import Graph
