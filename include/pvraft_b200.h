@@ -88,7 +88,8 @@ PVRAFT_API int pvraft_corr_reorder(const float* val_in, const int32_t* idx_in, i
  * Point-voxel correlation lookup (index + reduce part), one fused pass over the K candidates of
  * every point.  Replaces CorrBlock.get_voxel_feature up to (not incl.) out_conv, model/corr.py:47-71,
  * and CorrBlock.get_knn_feature up to (not incl.) knn_conv, model/corr.py:75-91.
- *   corr_val [B,N,K] f32, corr_idx [B,N,K] int32 (rows of xyz2), xyz2 [B,N,3], coords [B,N,3]
+ *   corr_val [B,N,K] f32, corr_idx [B,N,K] int32 (rows of xyz2), xyz2_pad [B,N,4] = (x,y,z,0) rows of the second cloud
+ *   (pvraft_xyz_pad_fwd, once per forward; 16-byte aligned, as corr_idx), coords [B,N,3]
  *   -> vox      [B,N,vox_ld]     (vox_ld >= levels*27, 0 = dense; pad columns are written as zeros so that the
  *                                consumer can read rows with 128-bit loads)  channel = level*27 + cell; mean corr of the candidates whose
  *                                round((xyz-coords)/r_level) lies in {-1,0,1}^3  (round-half-even,
@@ -101,10 +102,13 @@ PVRAFT_API int pvraft_corr_reorder(const float* val_in, const int32_t* idx_in, i
  *                                atomics into a buffer the caller has ZEROED: [0..3]=sum f_i, [4..13]=sum f_i f_j (i<=j,
  *                                row-major upper triangle), [14]=edge count, [15]=scratch (the kernel's work counter);
  *                                may be NULL (then the points are split statically)
- *   -> dbg_cube [B,N,K,levels] int8  cell id or -1 of every candidate (test hook; NULL in production)
+ *   -> dbg_cube [B,N,K,levels] int8  cell id or -1 of every candidate AS DERIVED BY THE FUSED KERNEL ITSELF (the coarsest-cube
+ *                                pre-test, the compaction and the per-level cell codes); test hook, NULL in production
  * K in {32,64,128,256,512,1024}; 1 <= levels <= 4; knn fixed at 32.
  * --------------------------------------------------------------------------------------------- */
-PVRAFT_API int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr_idx, const float* xyz2, const float* coords,
+/* xyz [rows,3] -> out [rows,4] = (x,y,z,0): the gather table of the lookup kernel (one 128-bit load per candidate). */
+PVRAFT_API int pvraft_xyz_pad_fwd(const float* xyz, int64_t rows, float* out, void* stream);
+PVRAFT_API int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr_idx, const float* xyz2_pad, const float* coords,
                            int B, int N, int K, int levels, float base_scale, float* vox, int vox_ld, float* knn_sel,
                            int32_t* knn_slot, double* moments, int8_t* dbg_cube, void* stream);
 

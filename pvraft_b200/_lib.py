@@ -71,6 +71,7 @@ _SIGNATURES = {
     'pvraft_corr_matmul_fwd': (C.c_int, [VP, VP, C.c_int, C.c_int, C.c_int, VP, VP, VP]),
     'pvraft_corr_topk_fwd': (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int, VP, VP, VP]),
     'pvraft_corr_reorder': (C.c_int, [VP, VP, C.c_int64, C.c_int, VP, VP, VP]),
+    'pvraft_xyz_pad_fwd': (C.c_int, [VP, C.c_int64, VP, VP]),
     'pvraft_corr_lookup_fwd': (C.c_int, [VP, VP, VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                          VP, C.c_int, VP, VP, VP, VP, VP]),
     'pvraft_linear_fwd': (C.c_int, [C.POINTER(LinearArgs), VP]),

@@ -57,6 +57,7 @@ class CorrBlock(nn.Module):
         self.corr_val = None     # [B,N,K] f32 correlation of the kept candidates (bank-aware order, see ops.corr_reorder)
         self.corr_idx = None     # [B,N,K] int32 candidate ids (rows of xyz2), same order
         self._xyz2 = None
+        self._xyz2p = None   # [B,N,4] (x,y,z,0): the lookup kernel's gather table
 
     # ------------------------------------------------------------------------------------------
     @staticmethod
@@ -95,12 +96,14 @@ class CorrBlock(nn.Module):
         val, idx = ops.corr_topk(corr, self.truncate_k)
         self.corr_val, self.corr_idx = ops.corr_reorder(val, idx)
         self._xyz2 = xyz2.detach().contiguous().float()
+        self._xyz2p = ops.xyz_pad(self._xyz2)
 
     def set_state(self, truncated_corr, corr_idx, xyz2):
         """Install an externally built state (tests / benchmarks): corr [B,N,K] f32, idx [B,N,K] int."""
         self.corr_val, self.corr_idx = ops.corr_reorder(truncated_corr.contiguous().float(),
                                                         corr_idx.contiguous().to(torch.int32))
         self._xyz2 = xyz2.contiguous().float()
+        self._xyz2p = ops.xyz_pad(self._xyz2)
 
     @property
     def truncated_corr(self):
@@ -123,7 +126,7 @@ class CorrBlock(nn.Module):
         """Index + reduce part of the lookup (pvraft_corr_lookup_fwd) -> dict(vox, knn_sel, moments, ...)."""
         if self.corr_val is None:
             raise RuntimeError('CorrBlock.init_module must run before the lookup')
-        return ops.corr_lookup(self.corr_val, self.corr_idx, self._xyz2, coords.detach().contiguous().float(),
+        return ops.corr_lookup(self.corr_val, self.corr_idx, self._xyz2p, coords.detach().contiguous().float(),
                                self.num_levels, self.base_scale, **kw)
 
     def feature_args(self, lk, y1, y1_stats, b, n):

@@ -4,46 +4,56 @@
 // CorrBlock.get_knn_feature up to knn_conv (model/corr.py:75-91) with ONE pass over the K
 // candidates of every point.  Data movement:
 //   * per-iteration HBM stream = 8 B per candidate (fp32 correlation + int32 candidate id); the
-//     reference's materialised [B,N,K,3] xyz tensor is replaced by a per-sample x/y/z table (3 x N floats)
-//     that a CTA stages once in shared memory and gathers from with 32-bit loads; pvraft_corr_reorder
-//     arranges every row once per forward so that the 32 lanes of a gather hit (nearly) distinct banks;
-//   * a warp owns a point; its 2 x K*4-byte row is brought into the warp's shared-memory stage by
-//     the TMA engine (cp.async.bulk + mbarrier complete_tx) while the warp is still reducing the
-//     previous point, so loads are in flight without holding registers.
+//     reference's materialised [B,N,K,3] xyz tensor is replaced by a per-sample table of 16-byte (x,y,z,0) rows
+//     (pvraft_xyz_pad_fwd, once per forward) that a CTA brings into shared memory with bulk copies (TMA) and gathers
+//     from with ONE 128-bit load per candidate; pvraft_corr_reorder arranges every row once per forward so that the
+//     lanes of a gather hit (nearly) distinct banks;
+//   * a warp owns a point; its K*4-byte candidate-id row is brought into the warp's shared-memory stage by
+//     the TMA engine (cp.async.bulk + mbarrier complete_tx) -- the row of the NEXT point is requested as soon as the
+//     streaming pass of the current one has consumed the stage; the correlation row is prefetched to L2 and read sparsely.
 // Per point the warp produces
-//   * the 27-cell x `levels` voxel means: candidates inside the coarsest cube (cheap sphere pre-test on
-//     the squared distance, exact test only for the survivors) are compacted in ascending candidate
-//     order into a small list; lanes 0..26 each own a cell and sum sequentially -> identical to a
-//     sequential scatter_add; the list is flushed whenever it fills, so dense cells need no extra smem;
-//   * the 32 nearest candidates: exact threshold on the fp32 distance bits by an interpolating
-//     bisection with warp-wide population counts (no sort), ties -> lowest slot;
+//   * the 27-cell x `levels` voxel means: candidates inside the coarsest cube (one compare against a host-derived
+//     threshold, exact) are compacted in ascending candidate order into a small list; in chunks of 32 entries, lane i
+//     derives the cell of entry i at every level, entries of one cell find each other with a warp match and add their
+//     correlations to the cell's shared-memory accumulator one rank at a time -> the sums equal a sequential
+//     scatter_add over the stored row bit for bit, at a cost that grows with the fullest cell, not with the list;
+//   * the 32 nearest candidates: exact threshold on the fp32 distance bits -- a 128-bin shared-memory histogram
+//     brackets it, a short bisection with warp-wide population counts finishes (no sort), ties -> lowest slot;
 //   * double-precision first/second moments of the kNN 4-vectors, from which the consumer derives the
 //     GroupNorm statistics of knn_conv's output without materialising its [B,64,N,32] tensor.
 // Index-deciding arithmetic is bit-faithful to the reference's fp32 op sequence: separate rn
 // subtract / multiply / add (no FMA contraction), true IEEE division, round-half-even.
+#include <math.h>
+
 #include "common.cuh"
 
 namespace pvraft {
 
 constexpr int kLookupThreads = 640;   // 20 warps: bounded by registers (<= 102/thread) and by shared memory
+constexpr int kAccCells = 128;        // >= 4 levels * 27 cells
 
-// per-warp shared memory: staged row (K*8) + valid-slot list (K*2) + one 32-entry chunk (256) + kNN slots (128) +
-// mbarrier (8); the 128-bin distance histogram of the kNN select (512 B) reuses the slot list; rounded to 128 B so that every warp's stage stays 128-byte aligned for the bulk copies
-__host__ __device__ constexpr size_t lookup_warp_bytes(int K) { return (((size_t)(K < 256 ? 256 : K) * 2 + (size_t)K * 8 + 256 + 128 + 16) + 127) & ~(size_t)127; }
+// per-warp shared memory: staged id row (K*4) + valid-slot list (K*2, >= 1 KB: the 128-bin distance histogram of the
+// kNN select and its 32 sink bins reuse it) + one 32-entry chunk (256) + kNN slots (128) + per-cell sums and counts (2 * 512) + mbarrier (16);
+// rounded to 128 B so that every warp's stage stays 128-byte aligned for the bulk copies
+__host__ __device__ constexpr size_t lookup_warp_bytes(int K) {
+    return (((size_t)(K < 512 ? 512 : K) * 2 + (size_t)K * 4 + 256 + 128 + 2 * kAccCells * 4 + 16) + 127) & ~(size_t)127;
+}
 
 struct LookupParams {
     const float* corr_val;
     const int32_t* corr_idx;
-    const float* xyz2;   // [B,N,3]
+    const float4* tab;   // [B,N] (x,y,z,0) rows of xyz2
     const float* coords; // [B,N,3]
     float* vox;          // [B,N,levels*27]
     float4* knn_sel;     // [B,N,32]
     int32_t* knn_slot;   // [B,N,32] or null
     double* moments;     // [B,16] or null
+    int8_t* dbg_cube;    // [B,N,K,levels] or null: the cell id (-1 = outside) this kernel derived for every candidate
     int B, N, K, levels;
     int vox_ld;          // floats per vox row (>= levels*27; the pad is zero-filled)
     float r[4];          // cell edge per level
     float inv_r[4];      // exact reciprocal when r is a power of two
+    float thr_c;         // max|d| < thr_c  <=>  |round(d / r_coarsest)| <= 1 on every axis (cube_threshold())
     int warps;           // warps per block actually carved in shared memory
     int chunk;           // points per dynamic work claim
 };
@@ -54,24 +64,16 @@ __device__ __forceinline__ float div_r(float d, float r, float inv_r) {
 }
 
 // cell id in [0,27) of offset (dx,dy,dz) at cell edge r, or 0xFF when outside the 3x3x3 cube
-// (model/corr.py:54-57: round((xyz - coords) / r), |.| <= 1 on all axes, (qx+1)*9+(qy+1)*3+(qz+1))
+// (model/corr.py:54-57: round((xyz - coords) / r), |.| <= 1 on all axes, (qx+1)*9+(qy+1)*3+(qz+1); the cell number is
+// formed in fp32 -- small integers, exact -- and converted once)
 template <bool POW2>
 __device__ __forceinline__ unsigned cell_code(float dx, float dy, float dz, float r, float inv_r) {
     const float qx = rintf(div_r<POW2>(dx, r, inv_r));
     const float qy = rintf(div_r<POW2>(dy, r, inv_r));
     const float qz = rintf(div_r<POW2>(dz, r, inv_r));
-    const bool ok = (fabsf(qx) <= 1.f) && (fabsf(qy) <= 1.f) && (fabsf(qz) <= 1.f);
-    const int cell = (int)(qx + 1.f) * 9 + (int)(qy + 1.f) * 3 + (int)(qz + 1.f);
+    const bool ok = fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) <= 1.f;
+    const int cell = (int)fmaf(qx, 9.f, fmaf(qy, 3.f, qz + 13.f));
     return ok ? (unsigned)cell : 0xFFu;
-}
-
-// xyz of candidate `id`: from the staged table (3 conflict-light 32-bit loads) or from global memory
-template <bool SMEM_TAB>
-__device__ __forceinline__ float3 gather_xyz(const float* __restrict__ s_tab, int n, const float* __restrict__ xyz_g, int id) {
-    // AoS [N][3]: word 3*id + c lives in bank (3*id + c) % 32, a bijection of id % 32 -> lanes with distinct
-    // id % 32 (what pvraft_corr_reorder arranges) never collide
-    if (SMEM_TAB) return make_float3(s_tab[3 * id], s_tab[3 * id + 1], s_tab[3 * id + 2]);
-    return make_float3(__ldg(xyz_g + 3 * (size_t)id), __ldg(xyz_g + 3 * (size_t)id + 1), __ldg(xyz_g + 3 * (size_t)id + 2));
 }
 
 // ---- mbarrier / bulk-copy (TMA) primitives ----------------------------------------------------------
@@ -104,23 +106,6 @@ __device__ __forceinline__ void prefetch_row(const float* row, int K, int lane) 
     for (int o = lane * 16; o < K; o += 32 * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
 }
 
-// lanes 0..26 own one cell of every level: sequential (ascending candidate) sums over a chunk of entries
-__device__ __forceinline__ void scan_chunk(const uint2* __restrict__ s_chunk, int n, int lane, float (&sum)[4], int (&cnt)[4]) {
-    const unsigned mine = (unsigned)lane * 0x01010101u;
-    for (int i = 0; i < n; ++i) {
-        const uint2 e = s_chunk[i];
-        const unsigned m = e.x ^ mine;   // byte l is zero iff the entry falls into this lane's cell at level l
-        const float val = __uint_as_float(e.y);
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            if ((m & (0xFFu << (8 * l))) == 0u) {
-                sum[l] = __fadd_rn(sum[l], val);
-                cnt[l] += 1;
-            }
-        }
-    }
-}
-
 // inclusive warp scan of a word of packed 8-bit counters (no field may exceed 255)
 __device__ __forceinline__ unsigned warp_scan_packed(unsigned w, int lane) {
 #pragma unroll
@@ -138,32 +123,32 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
     constexpr int K = KPL * 32;
     constexpr unsigned NIB = (1u << VEC) - 1u;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const size_t tab_bytes = SMEM_TAB ? (((size_t)p.N * 12 + 127) & ~(size_t)127) : 0;
-    float* s_tab = reinterpret_cast<float*>(smem_raw);   // [N][3], a verbatim copy of the sample's xyz2
+    const size_t tab_bytes = SMEM_TAB ? (((size_t)p.N * 16 + 127) & ~(size_t)127) : 0;
+    const float4* s_tab = reinterpret_cast<const float4*>(smem_raw);   // [N] (x,y,z,0), a verbatim copy of the sample's table
     const int w = warp_id(), lane = lane_id();
     unsigned char* wbase = smem_raw + tab_bytes + (size_t)w * lookup_warp_bytes(K);
-    int* s_stage = reinterpret_cast<int*>(wbase);                        // [2][K] double-buffered candidate-id rows
-    constexpr int VL = (K < 256 ? 256 : K) * 2;
-    unsigned short* s_vlist = reinterpret_cast<unsigned short*>(wbase + K * 8);   // [K] slots inside the coarsest cube
-    int* s_hist = reinterpret_cast<int*>(wbase + K * 8);                 // [128] kNN distance histogram (after the list is dead)
-    uint2* s_chunk = reinterpret_cast<uint2*>(wbase + K * 8 + VL);       // [32]  (cell codes, corr) of one chunk
-    int* s_slots = reinterpret_cast<int*>(wbase + K * 8 + VL + 256);     // [32]  kNN slots
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(wbase + K * 8 + VL + 384);   // [2]
+    int* s_stage = reinterpret_cast<int*>(wbase);                        // [K] candidate ids of the point being streamed
+    constexpr int VL = (K < 512 ? 512 : K) * 2;   // >= 640 B: 128 histogram bins + 32 per-lane sinks
+    unsigned short* s_vlist = reinterpret_cast<unsigned short*>(wbase + K * 4);   // [K] slots inside the coarsest cube
+    int* s_hist = reinterpret_cast<int*>(wbase + K * 4);                 // [128 + 32] kNN distance histogram (after the list is dead)
+    uint2* s_chunk = reinterpret_cast<uint2*>(wbase + K * 4 + VL);       // [32]  (cell codes, corr) of one chunk
+    int* s_slots = reinterpret_cast<int*>(wbase + K * 4 + VL + 256);     // [32]  kNN slots
+    float* s_acc = reinterpret_cast<float*>(wbase + K * 4 + VL + 384);   // [128] per-cell correlation sums, index level*27 + cell
+    int* s_cnt = reinterpret_cast<int*>(wbase + K * 4 + VL + 384 + kAccCells * 4);                      // [128] per-cell counts
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(wbase + K * 4 + VL + 384 + 2 * kAccCells * 4);
     pdl_trigger();   // the next kernel may be staged while this one drains
     const bool active_warp = w < p.warps;
-    __shared__ int s_next;   // next unclaimed point of the current segment (warps take points dynamically: per-point cost varies)
+    __shared__ int s_next;   // next unclaimed point of the current segment (static mode: warps take points dynamically)
+    __shared__ unsigned long long s_tabbar;
     // 1/c in double for c = 0..K: (float)(double(sum) * rcp[c]) is the correctly rounded fp32 quotient sum/c for
     // every integer c <= 2^20 (x/c is never within 2^-34 relative of a rounding boundary), without a division
     double* s_rcp = reinterpret_cast<double*>(smem_raw + tab_bytes + (size_t)p.warps * lookup_warp_bytes(K));
     for (int i = threadIdx.x; i <= K; i += blockDim.x) s_rcp[i] = i > 0 ? 1.0 / (double)i : 1.0;
 
-    if (active_warp && lane == 0) { mbar_init(s_bar, 1); mbar_init(s_bar + 1, 1); }
+    if (active_warp && lane == 0) mbar_init(s_bar, 1);
+    if (threadIdx.x == 0) mbar_init(&s_tabbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    // Launched with PDL: only the set-up above overlaps the previous kernel's tail.  Everything below reads what earlier
-    // kernels of the stream wrote -- the zeroed per-sample work counter (griddepcontrol.wait is what makes the
-    // predecessor's stores visible), the query coordinates -- or writes buffers they may still read.
-    pdl_wait();
 
     // Work distribution.  With a moment buffer (zeroed by the caller) and at least one CTA per sample, the CTAs of a sample
     // share its points dynamically: warps claim chunks of 4 consecutive points from a counter kept in the unused 16th moment
@@ -180,99 +165,117 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
         split_range(total, gridDim.x, blockIdx.x, pt_begin, pt_end);
     }
     const int L = p.levels;
-    const float rc = L == 1 ? p.r[0] : L == 2 ? p.r[1] : L == 3 ? p.r[2] : p.r[3];               // coarsest level
-    const float inv_rc = L == 1 ? p.inv_r[0] : L == 2 ? p.inv_r[1] : L == 3 ? p.inv_r[2] : p.inv_r[3];
-    unsigned phase0 = 0, phase1 = 0;
+    const int nvox = L * 27;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned phase = 0, tab_phase = 0;
+    bool waited = false;
     const int kChunk = p.chunk;
+    const unsigned one = (unsigned)min(p.chunk, 1);   // == 1, but not to the compiler (see the histogram below)
 
     long long seg = pt_begin;
     while (seg < pt_end) {
         const int b = (int)(seg / p.N);
         long long seg_end = (long long)(b + 1) * p.N;
         if (seg_end > pt_end) seg_end = pt_end;
-        const float* tab_g = p.xyz2 + (size_t)b * p.N * 3;
+        const float4* tab_g = p.tab + (size_t)b * p.N;
         int* counter = dyn ? reinterpret_cast<int*>(p.moments + (size_t)b * PVRAFT_MOMENTS + 15) : nullptr;
         auto claim_chunk = [&]() -> long long {   // first point of the next unclaimed chunk of this sample
             int c = 0;
             if (lane == 0) c = atomicAdd(counter, kChunk);
             return seg + __shfl_sync(kFull, c, 0);
         };
+        __syncthreads();   // previous segment's readers are done (table and point counter)
+        if (SMEM_TAB && threadIdx.x == 0) {
+            // the sample's table: N*16 bytes by the TMA engine (written once per forward, long before this launch, so the
+            // request may precede griddepcontrol.wait and overlap the previous kernel's tail)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const unsigned bytes = (unsigned)p.N * 16u;
+            mbar_expect_tx(&s_tabbar, bytes);
+            for (unsigned off = 0; off < bytes; off += 32768u)
+                bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char*>(tab_g) + off, min(32768u, bytes - off), &s_tabbar);
+        }
+        if (threadIdx.x == 0) s_next = 2 * p.warps;   // static mode: warp w starts with points w and w + warps
+        // Launched with PDL: only the set-up above overlaps the previous kernel's tail.  Everything below reads what
+        // earlier kernels of the stream wrote -- the zeroed per-sample work counter (griddepcontrol.wait is what makes
+        // the predecessor's stores visible), the query coordinates -- or writes buffers they may still read.
+        if (!waited) { pdl_wait(); waited = true; }
         // this warp's first two points
         long long pt0 = seg + w, nxt0 = seg + w + p.warps;
         int left0 = 0;   // points after nxt0 that remain in nxt0's chunk (dynamic mode)
         if (dyn && active_warp) { pt0 = claim_chunk(); nxt0 = pt0 + 1; left0 = kChunk - 2; }
-        // kick off this warp's first row, then stage the sample's xyz table while it is in flight
-        if (active_warp && pt0 < seg_end) {
+        if (active_warp && pt0 < seg_end) {   // kick off this warp's first row
             if (lane == 0) {
                 mbar_expect_tx(s_bar, K * 4);
                 bulk_g2s(s_stage, p.corr_idx + pt0 * K, K * 4, s_bar);
             }
             prefetch_row(p.corr_val + pt0 * K, K, lane);
         }
-        __syncthreads();   // previous segment's readers are done (table and point counter)
-        if (threadIdx.x == 0) s_next = 2 * p.warps;   // warp w starts with points w and w + warps
-        if (SMEM_TAB) {
-            for (int i = threadIdx.x; i < p.N * 3; i += blockDim.x) s_tab[i] = __ldg(tab_g + i);
-        }
-        __syncthreads();
+        if (SMEM_TAB) { mbar_wait(&s_tabbar, tab_phase); tab_phase ^= 1u; }
+        __syncthreads();   // s_next
         double mom[14];
 #pragma unroll
         for (int i = 0; i < 14; ++i) mom[i] = 0.0;
 
         if (active_warp) {
-            int cur = 0, left = left0, done = 0;
+            int left = left0, done = 0;
             long long nxt = nxt0;
-            for (long long pt = pt0; pt < seg_end; cur ^= 1, ++done) {
+            for (long long pt = pt0; pt < seg_end; ++done) {
                 const float cx = __ldg(p.coords + pt * 3 + 0);
                 const float cy = __ldg(p.coords + pt * 3 + 1);
                 const float cz = __ldg(p.coords + pt * 3 + 2);
-                const int* s_idx = s_stage + cur * K;
-                {   // the other stage is free (its point is finished): start the next row now, a whole point ahead
-                    if (nxt < seg_end) {
-                        if (lane == 0) {
-                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            mbar_expect_tx(s_bar + (cur ^ 1), K * 4);
-                            bulk_g2s(s_stage + (cur ^ 1) * K, p.corr_idx + nxt * K, K * 4, s_bar + (cur ^ 1));
-                        }
-                        prefetch_row(p.corr_val + nxt * K, K, lane);   // correlation row -> L2; read sparsely below
-                    }
-                }
-                if (cur == 0) { mbar_wait(s_bar, phase0); phase0 ^= 1u; } else { mbar_wait(s_bar + 1, phase1); phase1 ^= 1u; }
                 const float* rv = p.corr_val + pt * K;
+                const int32_t* ri = p.corr_idx + pt * K;
+                if (p.dbg_cube) {
+                    for (int i = lane; i < K * L; i += 32) p.dbg_cube[pt * K * L + i] = (int8_t)-1;
+                }
+                // per-cell accumulators of this point
+                *reinterpret_cast<float4*>(s_acc + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<int4*>(s_cnt + lane * 4) = make_int4(0, 0, 0, 0);
+                mbar_wait(s_bar, phase);
+                phase ^= 1u;
 
                 // ---- stream the staged row: slot(j,s) = j*32*VEC + lane*VEC + s -------------------------
                 unsigned dist[KPL];       // fp32 bits of the (non-negative) squared distance
                 unsigned valid_bits = 0;  // bit e: candidate e of this lane lies inside the coarsest 3x3x3 cube
+                const float thr = p.thr_c;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     int ci[VEC];
                     if (VEC == 4) {
-                        const int4 c = reinterpret_cast<const int4*>(s_idx)[j * 32 + lane];
+                        const int4 c = reinterpret_cast<const int4*>(s_stage)[j * 32 + lane];
                         ci[0] = c.x; ci[1 % VEC] = c.y; ci[2 % VEC] = c.z; ci[3 % VEC] = c.w;
                     } else {
 #pragma unroll
-                        for (int s = 0; s < VEC; ++s) ci[s] = s_idx[j * 32 * VEC + lane * VEC + s];
+                        for (int s = 0; s < VEC; ++s) ci[s] = s_stage[j * 32 * VEC + lane * VEC + s];
                     }
 #pragma unroll
                     for (int s = 0; s < VEC; ++s) {
-                        const float3 q = gather_xyz<SMEM_TAB>(s_tab, p.N, tab_g, ci[s]);
+                        const float4 q = SMEM_TAB ? s_tab[ci[s]] : __ldg(tab_g + ci[s]);
                         const float dx = __fsub_rn(q.x, cx), dy = __fsub_rn(q.y, cy), dz = __fsub_rn(q.z, cz);
                         const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
                         dist[j * VEC + s] = __float_as_uint(d2);
-                        // |round(d/r)| <= 1 on every axis  <=>  max|d|/r < 1.5 (round-half-even sends 1.5 to 2;
-                        // x -> fl(x/r) is monotone, so the max can be taken before the division)
+                        // |round(d/r)| <= 1 on every axis  <=>  fl(max|d| / r) < 1.5 (round-half-even sends 1.5 to 2;
+                        // x -> fl(x/r) is monotone)  <=>  max|d| < thr, thr = the smallest float whose quotient reaches 1.5
                         const float amax = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
-                        valid_bits |= (div_r<POW2>(amax, rc, inv_rc) < 1.5f ? 1u : 0u) << (j * VEC + s);
+                        valid_bits |= (amax < thr ? 1u : 0u) << (j * VEC + s);
                     }
+                }
+                __syncwarp();
+                // the stage is consumed (later id reads go to the L2-resident row): request the next point's row now
+                if (nxt < seg_end) {
+                    if (lane == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        mbar_expect_tx(s_bar, K * 4);
+                        bulk_g2s(s_stage, p.corr_idx + nxt * K, K * 4, s_bar);
+                    }
+                    prefetch_row(p.corr_val + nxt * K, K, lane);   // correlation row -> L2; read sparsely below
                 }
 
                 // ---- voxel means -----------------------------------------------------------------------
                 // (1) ordered compaction of the valid slots: one packed warp scan gives every lane its offset in
                 //     every block j, so the list is in ascending slot order (the order of a sequential scatter_add)
-                float sum[4] = {0.f, 0.f, 0.f, 0.f};
-                int cnt[4] = {0, 0, 0, 0};
-                int list_n = 0;
                 if (__any_sync(kFull, valid_bits != 0u)) {
+                    int list_n = 0;
                     unsigned w0 = 0, w1 = 0;
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
@@ -298,41 +301,57 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                         list_n += (int)tt;
                     }
                     __syncwarp();
-                    // (2) chunks of 32 entries: lane i derives the cell codes of entry i, then (3) the cell owners scan
+                    // (2) chunks of 32 entries: lane i derives the cells of entry i at every level; (3) the entries of one
+                    //     cell (warp match) add to its accumulator one rank at a time, lowest slot first
                     for (int c0 = 0; c0 < list_n; c0 += 32) {
                         const int n = min(32, list_n - c0);
+                        unsigned code = 0xFFFFFFFFu;
+                        float val = 0.f;
                         if (lane < n) {
                             const int slot = s_vlist[c0 + lane];
-                            const int id = s_idx[slot];
-                            const float3 q = gather_xyz<SMEM_TAB>(s_tab, p.N, tab_g, id);
+                            const int id = __ldg(ri + slot);
+                            val = __ldg(rv + slot);
+                            const float4 q = SMEM_TAB ? s_tab[id] : __ldg(tab_g + id);
                             const float dx = __fsub_rn(q.x, cx), dy = __fsub_rn(q.y, cy), dz = __fsub_rn(q.z, cz);
-                            unsigned code = 0xFFFFFFFFu;
 #pragma unroll
                             for (int l = 0; l < 4; ++l) {
                                 if (l < L) {
                                     const unsigned c = cell_code<POW2>(dx, dy, dz, p.r[l], p.inv_r[l]);
                                     code = (code & ~(0xFFu << (8 * l))) | (c << (8 * l));
+                                    if (p.dbg_cube) p.dbg_cube[(pt * K + slot) * L + l] = (int8_t)c;
                                 }
                             }
-                            s_chunk[lane] = make_uint2(code, __float_as_uint(__ldg(rv + slot)));
                         }
-                        __syncwarp();
-                        scan_chunk(s_chunk, n, lane, sum, cnt);
-                        __syncwarp();
+#pragma unroll
+                        for (int l = 0; l < 4; ++l) {
+                            if (l < L) {
+                                const unsigned c = (code >> (8 * l)) & 0xFFu;
+                                const bool act = c != 0xFFu;
+                                if (__any_sync(kFull, act)) {
+                                    const unsigned m = __match_any_sync(kFull, c);
+                                    const unsigned rank = __popc(m & lt_mask), gsize = __popc(m);
+                                    const unsigned maxg = __reduce_max_sync(kFull, act ? gsize : 0u);
+                                    const int cell = act ? l * 27 + (int)c : 0;
+                                    if (act && rank == 0u) s_cnt[cell] += (int)gsize;
+                                    for (unsigned r = 0; r < maxg; ++r) {
+                                        if (act && rank == r) s_acc[cell] = __fadd_rn(s_acc[cell], val);
+                                        __syncwarp();
+                                    }
+                                }
+                            }
+                        }
                     }
                 }
                 __syncwarp();
-                if (lane < p.vox_ld - L * 27) p.vox[pt * p.vox_ld + L * 27 + lane] = 0.f;   // zero the row padding
-                if (lane < 27) {
+                {   // sum / clamp(count, 1, N) (corr.py:65-66; rcp[0] = 1) of every cell, and zeros in the row padding
                     float* vo = p.vox + pt * p.vox_ld;
-#pragma unroll
-                    for (int l = 0; l < 4; ++l) {
-                        if (l < L) {
-                            // sum / clamp(count, 1, N) (corr.py:65-66); rcp[0] = 1
-                            vo[l * 27 + lane] = (float)((double)sum[l] * s_rcp[cnt[l]]);
-                        }
+                    for (int o = lane; o < p.vox_ld; o += 32) {
+                        float v = 0.f;
+                        if (o < nvox) v = (float)((double)s_acc[o] * s_rcp[s_cnt[o]]);
+                        vo[o] = v;
                     }
                 }
+                __syncwarp();
 
                 // ---- kNN: a threshold T with count(d <= T) >= 32 > count(d < T) ---------------------------
                 unsigned lmin = dist[0];
@@ -347,9 +366,15 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                     const unsigned base = hi > 0x01FFFFFFu ? hi - 0x01FFFFFFu : 0u;
                     *reinterpret_cast<int4*>(s_hist + lane * 4) = make_int4(0, 0, 0, 0);
                     __syncwarp();
+                    unsigned char* hist_b = reinterpret_cast<unsigned char*>(s_hist);
+                    const unsigned dummy = 512u + 4u * (unsigned)lane;   // bins 128..159: one private sink per lane
 #pragma unroll
                     for (int e = 0; e < KPL; ++e) {
-                        if (dist[e] <= hi) atomicAdd(s_hist + (dist[e] > base ? (dist[e] - base) >> 18 : 0u), 1);
+                        // bucket = (max(d, base) - base) >> 18, as a byte offset: ((.) >> 16) & ~3.  Candidates beyond `hi`
+                        // add to the lane's sink instead of being skipped: an `if` (or a predicated red) around a shared-memory
+                        // atomic compiles to a branch + reconvergence per candidate, 10 instructions instead of 7
+                        const unsigned off = ((max(dist[e], base) - base) >> 16) & 0x1FCu;
+                        atomicAdd(reinterpret_cast<unsigned*>(hist_b + (dist[e] <= hi ? off : dummy)), one);
                     }
                     __syncwarp();
                     const int4 h = *reinterpret_cast<const int4*>(s_hist + lane * 4);
@@ -433,8 +458,8 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                 {
                     const int slot = s_slots[lane];
                     const float c = __ldg(rv + slot);
-                    const int id = s_idx[slot];
-                    const float3 q = gather_xyz<SMEM_TAB>(s_tab, p.N, tab_g, id);
+                    const int id = __ldg(ri + slot);
+                    const float4 q = SMEM_TAB ? s_tab[id] : __ldg(tab_g + id);
                     const float dx = __fsub_rn(q.x, cx), dy = __fsub_rn(q.y, cy), dz = __fsub_rn(q.z, cz);
                     p.knn_sel[pt * 32 + lane] = make_float4(c, dx, dy, dz);
                     if (p.knn_slot) p.knn_slot[pt * 32 + lane] = slot;
@@ -445,7 +470,7 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                     mom[11] += f2 * f2; mom[12] += f2 * f3; mom[13] += f3 * f3;
                 }
                 __syncwarp();
-                // the point after next (its row is fetched while `nxt` is processed)
+                // the point after next (its row is requested once `nxt` has been streamed)
                 pt = nxt;
                 if (dyn) {
                     if (left > 0) { ++nxt; --left; } else { nxt = claim_chunk(); left = kChunk - 1; }
@@ -471,21 +496,10 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
     }
 }
 
-// Test hook: cell id (or -1) of every candidate at every level, same arithmetic as the fused kernel.
-template <bool POW2>
-__global__ void k_cube_debug(const LookupParams p, int8_t* __restrict__ out) {
+// (x,y,z) -> (x,y,z,0): the 16-byte rows the lookup kernel gathers with one 128-bit load
+__global__ void k_xyz_pad(const float* __restrict__ xyz, long long rows, float4* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)p.B * p.N * p.K;
-    if (i >= total) return;
-    const long long pt = i / p.K;
-    const int b = (int)(pt / p.N);
-    const float* q3 = p.xyz2 + ((size_t)b * p.N + p.corr_idx[i]) * 3;
-    const float3 q = make_float3(q3[0], q3[1], q3[2]);
-    const float dx = __fsub_rn(q.x, p.coords[pt * 3]), dy = __fsub_rn(q.y, p.coords[pt * 3 + 1]), dz = __fsub_rn(q.z, p.coords[pt * 3 + 2]);
-    for (int l = 0; l < p.levels; ++l) {
-        const unsigned c = cell_code<POW2>(dx, dy, dz, p.r[l], p.inv_r[l]);
-        out[i * p.levels + l] = c == 0xFFu ? (int8_t)-1 : (int8_t)c;
-    }
+    if (i < rows) out[i] = make_float4(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), 0.f);
 }
 
 // Bank-aware arrangement of one row's candidates (once per forward).  The lookup gathers x/y/z of 32
@@ -543,11 +557,22 @@ static bool is_pow2f(float r) {
     return r > 0.f && frexpf(r, &e) == 0.5f;
 }
 
+// The smallest float t with fl(t / r) >= 1.5 in IEEE fp32 division: since x -> fl(x / r) is monotone,
+// fl(x / r) < 1.5  <=>  x < t, and |round-half-even(fl(x / r))| <= 1  <=>  fl(|x| / r) < 1.5.  For a power-of-two r this is
+// 1.5 * r exactly; in general the search below walks at most a few ulps from that product.
+static float cube_threshold(float r) {
+    volatile float t = 1.5f * r;
+    auto q = [&](float x) { volatile float v = x / r; return (float)v; };
+    while (q(t) >= 1.5f) t = nextafterf(t, 0.f);
+    while (q(t) < 1.5f) t = nextafterf(t, INFINITY);
+    return t;
+}
+
 template <int KPL, bool POW2>
 static int launch_lookup(LookupParams& p, cudaStream_t st) {
     const int K = KPL * 32;
     const size_t per_warp = lookup_warp_bytes(K);
-    const size_t tab = (((size_t)p.N * 12 + 127) & ~(size_t)127);
+    const size_t tab = (((size_t)p.N * 16 + 127) & ~(size_t)127);
     const size_t rcp_bytes = (size_t)(K + 1) * sizeof(double) + 8;
     const bool smem_tab = tab + 8 * per_warp + rcp_bytes <= (size_t)kSmemBudget;
     const size_t avail = (size_t)kSmemBudget - (smem_tab ? tab : 0) - rcp_bytes;
@@ -598,17 +623,26 @@ extern "C" int pvraft_corr_reorder(const float* val_in, const int32_t* idx_in, i
     return check_launch("corr_reorder");
 }
 
-extern "C" int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr_idx, const float* xyz2,
+extern "C" int pvraft_xyz_pad_fwd(const float* xyz, int64_t rows, float* out, void* stream) {
+    if (!xyz || !out || rows <= 0) return fail(PVRAFT_ERR_BAD_ARG, "xyz_pad: bad argument");
+    k_xyz_pad<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(xyz, rows, reinterpret_cast<float4*>(out));
+    return check_launch("xyz_pad");
+}
+
+extern "C" int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr_idx, const float* xyz2_pad,
                                       const float* coords, int B, int N, int K, int levels, float base_scale,
                                       float* vox, int vox_ld, float* knn_sel, int32_t* knn_slot, double* moments,
                                       int8_t* dbg_cube, void* stream) {
-    if (!corr_val || !corr_idx || !xyz2 || !coords || !vox || !knn_sel) return fail(PVRAFT_ERR_BAD_ARG, "corr_lookup: null pointer");
+    if (!corr_val || !corr_idx || !xyz2_pad || !coords || !vox || !knn_sel) return fail(PVRAFT_ERR_BAD_ARG, "corr_lookup: null pointer");
     if (B <= 0 || N <= 0) return fail(PVRAFT_ERR_BAD_ARG, "corr_lookup: B=%d N=%d", B, N);
     if (levels < 1 || levels > 4) return fail(PVRAFT_ERR_UNSUPPORTED, "corr_lookup: levels=%d (1..4 supported)", levels);
     if (!(base_scale > 0.f)) return fail(PVRAFT_ERR_BAD_ARG, "corr_lookup: base_scale must be > 0");
+    if ((reinterpret_cast<uintptr_t>(xyz2_pad) & 15u) || (reinterpret_cast<uintptr_t>(corr_idx) & 15u))
+        return fail(PVRAFT_ERR_BAD_ARG, "corr_lookup: xyz2_pad and corr_idx must be 16-byte aligned (bulk copies)");
     LookupParams p{};
-    p.corr_val = corr_val; p.corr_idx = corr_idx; p.xyz2 = xyz2; p.coords = coords;
+    p.corr_val = corr_val; p.corr_idx = corr_idx; p.tab = reinterpret_cast<const float4*>(xyz2_pad); p.coords = coords;
     p.vox = vox; p.knn_sel = reinterpret_cast<float4*>(knn_sel); p.knn_slot = knn_slot; p.moments = moments;
+    p.dbg_cube = dbg_cube;
     p.B = B; p.N = N; p.K = K; p.levels = levels;
     p.vox_ld = vox_ld > 0 ? vox_ld : levels * 27;
     if (p.vox_ld < levels * 27 || p.vox_ld > levels * 27 + 32) return fail(PVRAFT_ERR_BAD_ARG, "corr_lookup: vox_ld=%d", vox_ld);
@@ -620,15 +654,8 @@ extern "C" int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr
         p.inv_r[l] = 1.0f / r;
         if (l < levels && !is_pow2f(r)) pow2 = false;
     }
+    p.thr_c = cube_threshold(p.r[levels - 1]);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dbg_cube) {
-        const long long total = (long long)B * N * K;
-        const unsigned blocks = (unsigned)((total + 255) / 256);
-        if (pow2) k_cube_debug<true><<<blocks, 256, 0, st>>>(p, dbg_cube);
-        else k_cube_debug<false><<<blocks, 256, 0, st>>>(p, dbg_cube);
-        int rc = check_launch("cube_debug");
-        if (rc) return rc;
-    }
 #define PVRAFT_LOOKUP_CASE(KPL_)                                                            \
     case KPL_ * 32:                                                                         \
         return pow2 ? launch_lookup<KPL_, true>(p, st) : launch_lookup<KPL_, false>(p, st);

@@ -106,9 +106,18 @@ def corr_topk(corr, k):
     return val, idx
 
 
-def corr_lookup(corr_val, corr_idx, xyz2, coords, levels, base_scale, vox=None, knn_sel=None, moments=None,
+def xyz_pad(xyz):
+    """[B,N,3] -> [B,N,4] = (x,y,z,0): the lookup kernel's gather table (one 128-bit load per candidate), built once per forward."""
+    b, n, _ = xyz.shape
+    out = torch.empty(b, n, 4, dtype=torch.float32, device=xyz.device)
+    _count(lib().pvraft_xyz_pad_fwd(_p(xyz), b * n, _p(out), _stream()), 'xyz_pad')
+    return out
+
+
+def corr_lookup(corr_val, corr_idx, xyz2_pad, coords, levels, base_scale, vox=None, knn_sel=None, moments=None,
                 want_slots=False, want_cube=False, vox_ld=None):
-    """-> dict(vox [B,N,pad4(levels*27)], knn_sel [B,N,32,4], moments [B,16] f64, [knn_slot], [cube])."""
+    """-> dict(vox [B,N,pad4(levels*27)], knn_sel [B,N,32,4], moments [B,16] f64, [knn_slot], [cube]).
+    `cube` [B,N,K,levels] int8 is the fused kernel's own cell decision for every candidate (test hook)."""
     b, n, k = corr_val.shape
     dev = corr_val.device
     if vox_ld is None:
@@ -121,7 +130,7 @@ def corr_lookup(corr_val, corr_idx, xyz2, coords, levels, base_scale, vox=None, 
         moments = new_stats(b, dev, 1).view(b, MOMENTS) if MOMENTS == 16 else torch.zeros(b, MOMENTS, dtype=torch.float64, device=dev)
     slots = torch.empty(b, n, KNN, dtype=torch.int32, device=dev) if want_slots else None
     cube = torch.empty(b, n, k, levels, dtype=torch.int8, device=dev) if want_cube else None
-    _count(lib().pvraft_corr_lookup_fwd(_p(corr_val), _p(corr_idx, torch.int32), _p(xyz2), _p(coords), b, n, k, levels,
+    _count(lib().pvraft_corr_lookup_fwd(_p(corr_val), _p(corr_idx, torch.int32), _p(xyz2_pad), _p(coords), b, n, k, levels,
                                         float(base_scale), _p(vox), vox.shape[-1], _p(knn_sel), _p(slots, torch.int32),
                                         _p(moments, torch.float64), _p(cube, torch.int8), _stream()), 'corr_lookup')
     return dict(vox=vox, knn_sel=knn_sel, moments=moments, knn_slot=slots, cube=cube)

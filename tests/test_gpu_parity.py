@@ -67,7 +67,7 @@ def test_lookup_against_oracle(dev, b, n, k, box, levels, scale):
     cb = block_with_state(state, xyz2, dev, levels, scale)
     assert_row_permutation(cb, state)
     state = stored_state(cb)
-    out = cb.lookup(coords.to(dev), want_slots=True, want_cube=True)
+    out = cb.lookup(coords.to(dev), want_slots=True, want_cube=True)   # cube: the FUSED kernel's own per-candidate cell decisions
     torch.cuda.synchronize()
     # (1) cube index + validity of EVERY candidate, bit-exact (model/corr.py:52-62)
     for lvl in range(levels):

@@ -38,7 +38,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     lib = _lib.lib()
     rc = lib.pvraft_corr_lookup_fwd(None, None, None, None, 1, 64, 64, 3, 0.25, None, 0, None, None, None, None, None)
     assert rc == -1 and b'null' in lib.pvraft_last_error_string()
-    rc = lib.pvraft_corr_lookup_fwd(8, 8, 8, 8, 1, 64, 96, 3, 0.25, 8, 0, 8, None, None, None, None)
+    rc = lib.pvraft_corr_lookup_fwd(16, 16, 16, 16, 1, 64, 96, 3, 0.25, 16, 0, 16, None, None, None, None)
     assert rc == -2 and b'truncate_k=96' in lib.pvraft_last_error_string()
     rc = lib.pvraft_knn_fwd(8, 8, 1, 16, 16, 33, 0, 8, None, None, None)
     assert rc == -2
