@@ -125,7 +125,9 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const size_t tab_bytes = SMEM_TAB ? (((size_t)p.N * 16 + 127) & ~(size_t)127) : 0;
     const float4* s_tab = reinterpret_cast<const float4*>(smem_raw);   // [N] (x,y,z,0), a verbatim copy of the sample's table
-    const int w = warp_id(), lane = lane_id();
+    const int w = warp_id();
+    int lane;   // pinned: left to itself the compiler re-derives threadIdx.x & 31 (S2R + LOP) ~9 times per point
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
     unsigned char* wbase = smem_raw + tab_bytes + (size_t)w * lookup_warp_bytes(K);
     int* s_stage = reinterpret_cast<int*>(wbase);                        // [K] candidate ids of the point being streamed
     constexpr int VL = (K < 512 ? 512 : K) * 2;   // >= 640 B: 128 histogram bins + 32 per-lane sinks
@@ -238,6 +240,8 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                 unsigned dist[KPL];       // fp32 bits of the (non-negative) squared distance
                 unsigned valid_bits = 0;  // bit e: candidate e of this lane lies inside the coarsest 3x3x3 cube
                 const float thr = p.thr_c;
+                unsigned long long cxy;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(cxy) : "f"(cx), "f"(cy));
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     int ci[VEC];
@@ -251,8 +255,19 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
 #pragma unroll
                     for (int s = 0; s < VEC; ++s) {
                         const float4 q = SMEM_TAB ? s_tab[ci[s]] : __ldg(tab_g + ci[s]);
-                        const float dx = __fsub_rn(q.x, cx), dy = __fsub_rn(q.y, cy), dz = __fsub_rn(q.z, cz);
-                        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                        // (dx,dy) and their squares as packed fp32x2 operations (one issue slot each; every component is an
+                        // IEEE round-to-nearest subtract / multiply, exactly the scalar sequence of model/corr.py:78-79)
+                        float dx, dy, sx, sy;
+                        {
+                            unsigned long long qxy, dxy, sxy;
+                            asm("mov.b64 %0, {%1, %2};" : "=l"(qxy) : "f"(q.x), "f"(q.y));
+                            asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dxy) : "l"(qxy), "l"(cxy));
+                            asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(sxy) : "l"(dxy));
+                            asm("mov.b64 {%0, %1}, %2;" : "=f"(dx), "=f"(dy) : "l"(dxy));
+                            asm("mov.b64 {%0, %1}, %2;" : "=f"(sx), "=f"(sy) : "l"(sxy));
+                        }
+                        const float dz = __fsub_rn(q.z, cz);
+                        const float d2 = __fadd_rn(__fadd_rn(sx, sy), __fmul_rn(dz, dz));
                         dist[j * VEC + s] = __float_as_uint(d2);
                         // |round(d/r)| <= 1 on every axis  <=>  fl(max|d| / r) < 1.5 (round-half-even sends 1.5 to 2;
                         // x -> fl(x/r) is monotone)  <=>  max|d| < thr, thr = the smallest float whose quotient reaches 1.5
@@ -345,11 +360,13 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                 __syncwarp();
                 {   // sum / clamp(count, 1, N) (corr.py:65-66; rcp[0] = 1) of every cell, and zeros in the row padding
                     float* vo = p.vox + pt * p.vox_ld;
-                    for (int o = lane; o < p.vox_ld; o += 32) {
-                        float v = 0.f;
-                        if (o < nvox) v = (float)((double)s_acc[o] * s_rcp[s_cnt[o]]);
-                        vo[o] = v;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {   // columns 0..95 (3 levels: 81 cells + the padding of the 96-wide layout)
+                        const int o = lane + 32 * i;
+                        const float v = (float)((double)s_acc[o] * s_rcp[s_cnt[o]]);   // cells >= nvox were never touched: 0 * 1
+                        if (o < p.vox_ld) vo[o] = v;
                     }
+                    for (int o = lane + 96; o < p.vox_ld; o += 32) vo[o] = o < nvox ? (float)((double)s_acc[o] * s_rcp[s_cnt[o]]) : 0.f;
                 }
                 __syncwarp();
 
@@ -481,15 +498,27 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                 }
             }
             if (p.moments) {
-#pragma unroll 1
-                for (int i = 0; i < 14; ++i) {
-                    double v = 0.0;
+                // 16 per-lane partial sums -> one total per lane pair with a reduce-scatter butterfly (15 + 1 double shuffles
+                // instead of 14 x 5): after the step with partner lane ^ d a lane keeps the half of its values selected by that
+                // bit of its id, so lane l ends up with the total of value ((l >> 1) & 15)
+                double v[16];
 #pragma unroll
-                    for (int q = 0; q < 14; ++q) v = q == i ? mom[q] : v;
-                    const double s = warp_sum(v);
-                    if (lane == 0 && s != 0.0) atomicAdd(p.moments + (size_t)b * PVRAFT_MOMENTS + i, s);
+                for (int i = 0; i < 14; ++i) v[i] = mom[i];
+                v[14] = (double)done;   // x 32 lanes = the number of kNN edges this warp produced
+                v[15] = 0.0;
+#pragma unroll
+                for (int d = 16, h = 8; d >= 2; d >>= 1, h >>= 1) {
+                    const bool up = (lane & d) != 0;
+#pragma unroll
+                    for (int i = 0; i < h; ++i) {
+                        const double send = up ? v[i] : v[i + h];
+                        const double keep = up ? v[i + h] : v[i];
+                        v[i] = keep + __shfl_xor_sync(kFull, send, d);
+                    }
                 }
-                if (lane == 0 && done > 0) atomicAdd(p.moments + (size_t)b * PVRAFT_MOMENTS + 14, (double)done * 32.0);
+                v[0] += __shfl_xor_sync(kFull, v[0], 1);
+                const int which = (lane >> 1) & 15;
+                if ((lane & 1) == 0 && which < 15 && v[0] != 0.0) atomicAdd(p.moments + (size_t)b * PVRAFT_MOMENTS + which, v[0]);
             }
         }
         seg = seg_end;
@@ -502,50 +531,64 @@ __global__ void k_xyz_pad(const float* __restrict__ xyz, long long rows, float4*
     if (i < rows) out[i] = make_float4(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), 0.f);
 }
 
-// Bank-aware arrangement of one row's candidates (once per forward).  The lookup gathers x/y/z of 32
-// candidates per instruction: slots {j*32*VEC + lane*VEC + s} for a fixed (j,s).  A stable counting sort by
-// (id mod 32), dealt round-robin over the KPL (j,s) groups, leaves every group with (nearly) one candidate per
-// shared-memory bank.  One warp per row; deterministic (ranks come from warp match, not from atomics).
+// Bank-aware arrangement of one row's candidates (once per forward).  The lookup gathers the 16-byte table rows of 32
+// candidates per instruction (slots {j*32*VEC + lane*VEC + s} for a fixed (j,s)); a 128-bit shared-memory load is served one
+// quarter-warp (8 lanes x 16 B = all 32 banks) at a time, so it is conflict-free when the 8 ids of every aligned group of 8
+// lanes are distinct modulo 8.  Candidates are ranked inside their class (id mod 8) in stable order; the k-th member of class c
+// goes to lane c + 8*(k mod 4) of gather group k/4.  A class holds K/8 such places; members beyond that (a random row is a few
+// per class over) fill the places the smaller classes leave free, in order.  One warp per row; deterministic (ranks come
+// from warp match, not from atomics).
 template <int KPL>
 __global__ void __launch_bounds__(256) k_corr_reorder(const float* __restrict__ val_in, const int32_t* __restrict__ idx_in,
                                                        long long rows, float* __restrict__ val_out, int32_t* __restrict__ idx_out) {
     constexpr int VEC = KPL >= 4 ? 4 : KPL;
     constexpr int K = KPL * 32;
-    __shared__ int s_cur[8][32];
+    constexpr int CAP = 4 * KPL;   // places per class
+    __shared__ int s_cur[8][32];   // per warp: [0..7] class counts, [8..15] free places before class c, [16..23] overflow before class c
     const int lane = lane_id(), w = warp_id();
     const long long row = (long long)blockIdx.x * 8 + w;
     if (row >= rows) return;
     const unsigned lt_mask = (1u << lane) - 1u;
     float v[KPL];
     int id[KPL];
+    int rank[KPL];
     s_cur[w][lane] = 0;
     __syncwarp();
 #pragma unroll
     for (int e = 0; e < KPL; ++e) {
         v[e] = __ldg(val_in + row * K + e * 32 + lane);
         id[e] = __ldg(idx_in + row * K + e * 32 + lane);
-        atomicAdd(&s_cur[w][id[e] & 31], 1);   // counts only: their value does not depend on the order of the adds
+        const int c = id[e] & 7;
+        const unsigned m = __match_any_sync(kFull, c);
+        rank[e] = s_cur[w][c] + __popc(m & lt_mask);   // stable: input order e*32 + lane
+        __syncwarp();
+        if (lane == __ffs(m) - 1) s_cur[w][c] += __popc(m);
+        __syncwarp();
     }
-    __syncwarp();
-    const int mycount = s_cur[w][lane];   // lane r: number of candidates with id % 32 == r
-    __syncwarp();
-    int start = mycount;   // exclusive scan over residues
+    {
+        const int n = lane < 8 ? s_cur[w][lane] : 0;
+        const int fr = lane < 8 ? max(0, CAP - n) : 0, ov = lane < 8 ? max(0, n - CAP) : 0;
+        int f = fr, o = ov;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int a = __shfl_up_sync(kFull, start, o);
-        if (lane >= o) start += a;
+        for (int d = 1; d < 8; d <<= 1) {
+            const int a = __shfl_up_sync(kFull, f, d), c = __shfl_up_sync(kFull, o, d);
+            if (lane >= d) { f += a; o += c; }
+        }
+        if (lane < 8) { s_cur[w][8 + lane] = f - fr; s_cur[w][16 + lane] = o - ov; }
     }
-    s_cur[w][lane] = start - mycount;
     __syncwarp();
 #pragma unroll
     for (int e = 0; e < KPL; ++e) {
-        const int r = id[e] & 31;
-        const unsigned m = __match_any_sync(kFull, r);
-        const int pos = s_cur[w][r] + __popc(m & lt_mask);
-        __syncwarp();
-        if (lane == __ffs(m) - 1) s_cur[w][r] += __popc(m);
-        __syncwarp();
-        const int g = pos % KPL, ln = pos / KPL;
+        int c = id[e] & 7, k = rank[e];
+        if (k >= CAP) {   // overflow member number oi of the row takes the oi-th free place
+            const int oi = s_cur[w][16 + c] + (k - CAP);
+            int cc = 0;
+#pragma unroll
+            for (int q = 1; q < 8; ++q) cc = s_cur[w][8 + q] <= oi && s_cur[w][q] < CAP ? q : cc;   // last class whose free run starts at or before oi
+            c = cc;
+            k = s_cur[w][cc] + (oi - s_cur[w][8 + cc]);
+        }
+        const int g = k >> 2, ln = c + 8 * (k & 3);
         const int slot = (g / VEC) * 32 * VEC + ln * VEC + (g % VEC);
         val_out[row * K + slot] = v[e];
         idx_out[row * K + slot] = id[e];

@@ -33,7 +33,7 @@ for b, n, k, box in cases:
     idx = ((start + torch.arange(k, device=dev).view(1, 1, k) * step) % n).to(torch.int32).contiguous()
     coords = xyz2[:, torch.randperm(n, device=dev, generator=g)] + 0.2 * (torch.rand(b, n, 3, device=dev, generator=g) * 2 - 1)
     corr = torch.sort(torch.randn(b, n, k, device=dev, generator=g) * 5 + 20, dim=2, descending=True).values.contiguous()
-    tab = xyz2.contiguous()
+    tab = ops.xyz_pad(xyz2.contiguous())
     corr, idx = ops.corr_reorder(corr, idx)
     coords = coords.contiguous()
     out = ops.corr_lookup(corr, idx, tab, coords, 3, 0.25)
@@ -43,6 +43,7 @@ for b, n, k, box in cases:
     evs = []
     for _ in range(a.reps):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        out['moments'].zero_()   # also holds the kernel's per-sample work counter
         s.record()
         ops.corr_lookup(corr, idx, tab, coords, 3, 0.25, vox=out['vox'], knn_sel=out['knn_sel'], moments=out['moments'])
         e.record()
