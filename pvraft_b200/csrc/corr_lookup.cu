@@ -103,7 +103,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 
 // bring a K-float row into L2 (64 B per lane per step); it is read sparsely (valid + kNN slots) afterwards
 __device__ __forceinline__ void prefetch_row(const float* row, int K, int lane) {
-    for (int o = lane * 16; o < K; o += 32 * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+    if (K <= 512) {   // one 64-byte piece per lane covers the row
+        if (lane * 16 < K) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + lane * 16));
+    } else {
+        for (int o = lane * 16; o < K; o += 32 * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+    }
 }
 
 // inclusive warp scan of a word of packed 8-bit counters (no field may exceed 255)
@@ -133,7 +137,6 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
     constexpr int VL = (K < 512 ? 512 : K) * 2;   // >= 640 B: 128 histogram bins + 32 per-lane sinks
     unsigned short* s_vlist = reinterpret_cast<unsigned short*>(wbase + K * 4);   // [K] slots inside the coarsest cube
     int* s_hist = reinterpret_cast<int*>(wbase + K * 4);                 // [128 + 32] kNN distance histogram (after the list is dead)
-    uint2* s_chunk = reinterpret_cast<uint2*>(wbase + K * 4 + VL);       // [32]  (cell codes, corr) of one chunk
     int* s_slots = reinterpret_cast<int*>(wbase + K * 4 + VL + 256);     // [32]  kNN slots
     float* s_acc = reinterpret_cast<float*>(wbase + K * 4 + VL + 384);   // [128] per-cell correlation sums, index level*27 + cell
     int* s_cnt = reinterpret_cast<int*>(wbase + K * 4 + VL + 384 + kAccCells * 4);                      // [128] per-cell counts
@@ -623,7 +626,7 @@ static int launch_lookup(LookupParams& p, cudaStream_t st) {
     if (warps > kLookupThreads / 32) warps = kLookupThreads / 32;
     if (warps < 1) return fail(PVRAFT_ERR_SMEM, "corr_lookup: K=%d does not fit shared memory", K);
     p.warps = warps;
-    p.chunk = 4;   // in-situ sweep at B=8, N=8192: 1 -> 0.137 ms, 2 -> 0.129, 3 -> 0.127, 4 -> 0.127, 8 -> 0.129, 16 -> 0.154, 32 -> 0.161
+    p.chunk = 2;   // in-situ sweep at B=8, N=8192 (v8 kernel): 1 -> 108.4 us, 2 -> 102.6, 3 -> 103.3, 4 -> 103.8, 6 -> 105.0, 8 -> 105.3
     if (const char* e = getenv("PVRAFT_LOOKUP_CHUNK")) { const int v = atoi(e); if (v >= 1 && v <= 64) p.chunk = v; }
     const size_t rcp = (size_t)(K + 1) * sizeof(double) + 8;
     const size_t smem = (smem_tab ? tab : 0) + warps * per_warp + rcp;
