@@ -363,6 +363,52 @@ PVRAFT_API int pvraft_knn_fwd(const float* xyz, const float* query, int B, int N
  * workspace: pvraft_knn_workspace_bytes(B, N) bytes. */
 PVRAFT_API int pvraft_point_order_fwd(const float* xyz, int B, int N, int32_t* perm, void* workspace, void* stream);
 
+/* ================================================================================================
+ * Gradient contract: what tools/engine.py:131-147 differentiates through.
+ * The training path runs layer by layer; each backward entry point below pairs with a forward one.
+ * Parameter-gradient outputs are ACCUMULATED with atomics into buffers the caller has zeroed.
+ * ============================================================================================= */
+
+/* 1x1 convolution (pvraft_linear_fwd without prologue / activation), weight and bias gradient:
+ *   x [rows,cin], dy [rows,cout]  ->  dW[o,i] += sum_r dy[r,o] x[r,i]  (row stride dw_ld floats, 0 = cin),  db[o] += sum_r dy[r,o] (or NULL).
+ * The data gradient dx = dy . W is pvraft_linear_fwd with the transposed weight.  cin <= 256, cout <= 128. */
+PVRAFT_API int pvraft_linear_wgrad(const float* x, const float* dy, int64_t rows, int cin, int cout, float* dW, int dw_ld, float* db,
+                        void* stream);
+
+/* GroupNorm(8) + activation backward (model/corr.py:17-18,25-26; model/flot/gconv.py:27-36 via autograd in the reference):
+ *   x, dy [B,rows,C]; stats [B,8,2] raw sums of x (as produced in the forward); count = rows * C/8; act/slope as pvraft_gn_act_fwd
+ *   -> dx [B,rows,C]; dgamma, dbeta [C] double (accumulated); dslope [1] double (PReLU slope gradient, or NULL);
+ *      gsum [B,8,2] double scratch, ZEROED by the caller. */
+PVRAFT_API int pvraft_gn_act_bwd(const float* x, const float* dy, const double* stats, const float* gamma, const float* beta, double count,
+                      int act, float slope, int B, int64_t rows, int C, double* gsum, double* dgamma, double* dbeta, double* dslope,
+                      float* dx, void* stream);
+
+/* SetConv edge stage, layer-wise (model/flot/gconv.py:65-73, fc1 factorised as in pvraft_setconv_edge_fwd):
+ *   forward : E[b,n,j,:] <- P[b,nbr[b,n,j],:] - P[b,n,:] + E[b,n,j,:]  (in place; E = W_e . edge_feats from pvraft_linear_fwd),
+ *             stats [B,8,2] accumulated sums of the result (or NULL)
+ *   backward: dP[b,nbr,:] += dT[b,n,j,:]; dP[b,n,:] -= sum_j dT[b,n,j,:]   (dP zeroed by the caller; dE = dT)
+ *   P [B,N,C], nbr [B,N,32] int32 local ids, E/dT [B,N,32,C]. */
+PVRAFT_API int pvraft_edge_fwd(const float* P, const int32_t* nbr, float* E, int B, int N, int C, double* stats, void* stream);
+PVRAFT_API int pvraft_edge_bwd(const float* dT, const int32_t* nbr, int B, int N, int C, float* dP, void* stream);
+
+/* max over the 32 neighbours (model/flot/gconv.py:80, model/corr.py:92): x [pts,32,C] -> y [pts,C], arg [pts,C] uint8 (first
+ * maximum); backward writes dx [pts,32,C] = dy at arg, 0 elsewhere. */
+PVRAFT_API int pvraft_maxk_fwd(const float* x, int64_t pts, int C, float* y, uint8_t* arg, void* stream);
+PVRAFT_API int pvraft_maxk_bwd(const float* dy, const uint8_t* arg, int64_t pts, int C, float* dx, void* stream);
+
+/* Backward of pvraft_corr_lookup_fwd w.r.t. corr_val (model/corr.py:47-66,84; indices and coordinates carry no gradient:
+ * corr.py:52-62 is under no_grad and RAFTSceneFlow.py:41 detaches the coordinates):
+ *   g_vox [B,N,vox_ld], g_sel [B,N,32,4] (channel 0 used), knn_slot [B,N,32] from the forward -> d_corr [B,N,K] (overwritten). */
+PVRAFT_API int pvraft_corr_lookup_bwd(const int32_t* corr_idx, const float* xyz2_pad, const float* coords, const int32_t* knn_slot,
+                           const float* g_vox, int vox_ld, const float* g_sel, int B, int N, int K, int levels, float base_scale,
+                           float* d_corr, void* stream);
+
+/* Backward of the truncated correlation (model/corr.py:95-100 + the top-k gather of :37-38), sparse over the K kept entries:
+ *   g [B,N,K], idx [B,N,K] (same stored order), fmap1/fmap2 [B,N,C] point-major
+ *   -> d_fmap1 [B,N,C] (overwritten), d_fmap2 [B,N,C] (ACCUMULATED, zeroed by the caller).  C in {32,64,128,256}. */
+PVRAFT_API int pvraft_corr_init_bwd(const float* g, const int32_t* idx, const float* fmap1, const float* fmap2, int B, int N, int C, int K,
+                         float* d_fmap1, float* d_fmap2, void* stream);
+
 /* sizeof() of the argument structs as compiled into the library (0 = linear, 1 = corrfeat, 2 = gru,
  * 3 = flowout, 4 = tc_linear; -1 otherwise): lets a foreign-language binding verify its struct layout at load time. */
 PVRAFT_API int pvraft_sizeof(int which);

@@ -327,6 +327,7 @@ def raft_loop(P: Params, li: LoopInputs, xyz1: torch.Tensor, num_iters: int, num
     coords1, coords2, net = xyz1, xyz1, li.net
     flows = []
     for _ in range(num_iters):
+        coords2 = coords2.detach()                                              # RAFTSceneFlow.py:41 (no gradient through the query)
         corr = corr_lookup(P, li.state, coords2, num_levels, base_scale)
         flow = coords2 - coords1
         net, delta = update_block(P, net, li.inp, corr, flow, li.graph)

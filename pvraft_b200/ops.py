@@ -333,6 +333,71 @@ def knn(xyz, query, k, mode=0, want_rel=False, use_sweep=True):
     return (out, rel) if want_rel else out
 
 
+# ---- gradient contract (include/pvraft_b200.h, "Gradient contract"): thin wrappers used by pvraft_b200/train.py ------------
+def linear_wgrad(x, dy, dw, db=None):
+    """dw [cout,cin] += dy^T x, db [cout] += column sums of dy (both zeroed by the caller); x [B,R,cin], dy [B,R,cout]."""
+    rows = x.shape[0] * x.shape[1]
+    _count(lib().pvraft_linear_wgrad(_p(x), _p(dy), rows, x.shape[-1], dy.shape[-1], _p(dw), dw.shape[-1], _p(db), _stream()),
+           'linear_wgrad')
+
+
+def gn_act_bwd(x, dy, stats, gamma, beta, count, act, slope, want_dslope=False):
+    """-> (dx, dgamma [C] f32, dbeta [C] f32, dslope [1] f32 or None)."""
+    b, rows, c = x.shape
+    dev = x.device
+    scratch = torch.zeros(b * 16 + 2 * c + 1, dtype=torch.float64, device=dev)   # gsum | dgamma | dbeta | dslope
+    gsum, dgamma, dbeta, dslope = scratch[:b * 16], scratch[b * 16:b * 16 + c], scratch[b * 16 + c:b * 16 + 2 * c], scratch[-1:]
+    dx = torch.empty_like(x)
+    _count(lib().pvraft_gn_act_bwd(_p(x), _p(dy), _p(stats, torch.float64), _p(gamma), _p(beta), float(count), act, float(slope), b, rows,
+                                   c, gsum.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), dslope.data_ptr() if want_dslope else None,
+                                   _p(dx), _stream()), 'gn_act_bwd')
+    return dx, dgamma.float(), dbeta.float(), (dslope.float() if want_dslope else None)
+
+
+def edge_fwd(p, nbr, e, stats=None):
+    """e [B,N*32,C] <- p[nbr] - p[centre] + e in place; stats [B,8,2] f64 accumulated."""
+    b, n, c = p.shape
+    _count(lib().pvraft_edge_fwd(_p(p), _p(nbr, torch.int32), _p(e), b, n, c, _p(stats, torch.float64), _stream()), 'edge_fwd')
+    return e
+
+
+def edge_bwd(dt, nbr, dp):
+    b, n, c = dp.shape
+    _count(lib().pvraft_edge_bwd(_p(dt), _p(nbr, torch.int32), b, n, c, _p(dp), _stream()), 'edge_bwd')
+    return dp
+
+
+def maxk_fwd(x, pts, c):
+    y = torch.empty(pts, c, dtype=torch.float32, device=x.device)
+    arg = torch.empty(pts, c, dtype=torch.uint8, device=x.device)
+    _count(lib().pvraft_maxk_fwd(_p(x), pts, c, _p(y), _p(arg, torch.uint8), _stream()), 'maxk_fwd')
+    return y, arg
+
+
+def maxk_bwd(dy, arg, pts, c):
+    dx = torch.empty(pts, KNN, c, dtype=torch.float32, device=dy.device)
+    _count(lib().pvraft_maxk_bwd(_p(dy), _p(arg, torch.uint8), pts, c, _p(dx), _stream()), 'maxk_bwd')
+    return dx
+
+
+def corr_lookup_bwd(corr_idx, xyz2_pad, coords, slots, g_vox, g_sel, levels, base_scale):
+    b, n, k = corr_idx.shape
+    d_corr = torch.empty(b, n, k, dtype=torch.float32, device=corr_idx.device)
+    _count(lib().pvraft_corr_lookup_bwd(_p(corr_idx, torch.int32), _p(xyz2_pad), _p(coords), _p(slots, torch.int32), _p(g_vox),
+                                        g_vox.shape[-1], _p(g_sel), b, n, k, levels, float(base_scale), _p(d_corr), _stream()),
+           'corr_lookup_bwd')
+    return d_corr
+
+
+def corr_init_bwd(g, idx, fmap1, fmap2):
+    b, n, c = fmap1.shape
+    d1 = torch.empty_like(fmap1)
+    d2 = torch.zeros_like(fmap2)
+    _count(lib().pvraft_corr_init_bwd(_p(g), _p(idx, torch.int32), _p(fmap1), _p(fmap2), b, n, c, g.shape[-1], _p(d1), _p(d2), _stream()),
+           'corr_init_bwd')
+    return d1, d2
+
+
 def device_info():
     sm, smem = C.c_int(0), C.c_int(0)
     check(lib().pvraft_device_info(C.byref(sm), C.byref(smem)), 'device_info')

@@ -11,7 +11,7 @@ import os
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import ops, train
 from .corr import CorrBlock
 from .extractor import FlotEncoder
 from .graph import Graph
@@ -19,11 +19,10 @@ from .refine import FlotRefine
 from .update import UpdateBlock
 
 
-def _require_inference(module):
-    if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
-        raise NotImplementedError(
-            'pvraft_b200: the backward kernels are not built yet -- run the forward under torch.no_grad() '
-            '(inference / evaluation).  Training support is the next row of DESIGN.md.')
+def _records_grad(module):
+    """True when the caller differentiates through this forward (tools/engine.py:140-143): the training path of train.py runs;
+    otherwise (torch.no_grad(), or nothing requires grad) the fused inference kernels do."""
+    return torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())
 
 
 class _RaftBase(nn.Module):
@@ -72,12 +71,16 @@ class _RaftBase(nn.Module):
         return static_out.clone() if torch.is_tensor(static_out) else [t.clone() for t in static_out]
 
     def forward(self, p, num_iters=12):
-        _require_inference(self)
-        if self.use_cuda_graph and p[0].is_cuda:
-            return self._graphed(p, num_iters)
-        return self._forward_impl(p, num_iters)
+        if not p[0].is_cuda:
+            raise ops._lib.PvraftError('pvraft_b200 kernels need CUDA tensors (no CPU fallback exists)')
+        with torch.cuda.device(p[0].device):        # the library launches on the current device
+            if _records_grad(self):
+                return self._forward_train(p, num_iters)
+            if self.use_cuda_graph:
+                return self._graphed(p, num_iters)
+            return self._forward_impl(p, num_iters)
 
-    def _encode(self, p):
+    def _encode(self, p, allow_sort=True):
         xyz1, xyz2 = p[0], p[1]
         if xyz1.dim() != 3 or xyz1.shape[-1] != 3 or xyz1.shape != xyz2.shape:
             raise ValueError('expected p = [xyz1 [B,N,3], xyz2 [B,N,3]]')
@@ -87,7 +90,7 @@ class _RaftBase(nn.Module):
         # meaning): along a Morton curve the 32 neighbour rows that the SetConv edge kernel gathers for consecutive points
         # overlap in L1/L2 (edge kernel 101 -> 83 us).  The flows are written back in the caller's order (`row_map`).
         self._row_map = None
-        if self.sort_points and ops.tc_supported(xyz1.shape[1]):
+        if self.sort_points and allow_sort and ops.tc_supported(xyz1.shape[1]):
             perm = ops.point_order(xyz1)
             xyz1 = torch.gather(xyz1, 1, perm.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
             offs = (torch.arange(xyz1.shape[0], device=xyz1.device) * xyz1.shape[1]).view(-1, 1)
@@ -169,6 +172,9 @@ class RSF(_RaftBase):
         _, preds = self._iterate(xyz1, graph_context, net, inp, num_iters, keep_all=True)
         return preds
 
+    def _forward_train(self, p, num_iters=12):
+        return train.rsf_forward(self, p, num_iters)
+
 
 class RSF_refine(_RaftBase):
     def __init__(self, args):
@@ -186,3 +192,11 @@ class RSF_refine(_RaftBase):
         xyz1, _, graph, graph_context, net, inp = self._encode(p)
         flow, _ = self._iterate(xyz1, graph_context, net, inp, num_iters, keep_all=False)
         return self._to_input_order(self.refine_block(flow, graph))      # RAFTSceneFlowRefine.py:46
+
+    def _forward_train(self, p, num_iters=12):
+        """model/RAFTSceneFlowRefine.py:22-48: everything up to the last flow under no_grad (the fused inference kernels),
+        the refiner -- the only part tools/engine_refine.py trains -- layer by layer with gradients."""
+        with torch.no_grad():
+            xyz1, _, graph, graph_context, net, inp = self._encode(p, allow_sort=False)
+            flow, _ = self._iterate(xyz1, graph_context, net, inp, num_iters, keep_all=False)
+        return train.flot_refine(self.refine_block, flow, graph)

@@ -86,7 +86,7 @@ def test_no_cpu_fallback():
     pc, pc2 = O.synthetic_clouds(1, 64)
     with torch.no_grad(), pytest.raises(_lib.PvraftError):
         m([pc, pc2], 1)
-    with pytest.raises(NotImplementedError):             # training needs the (unbuilt) backward kernels
+    with pytest.raises(_lib.PvraftError):                # the training path has no CPU fallback either
         m([pc, pc2], 1)
 
 
