@@ -50,7 +50,12 @@ class LinearFn(torch.autograd.Function):
     def backward(ctx, dy, *unused):
         x, w2 = ctx.saved_tensors
         dy = dy.contiguous()
-        dx = ops.linear(dy, w2.t().contiguous()) if ctx.needs_input_grad[0] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            # dx = dy . W: the same kernel with the transposed weight, 128 output columns (the kernel's limit) at a time
+            cin = w2.shape[1]
+            parts = [ops.linear(dy, w2[:, c0:min(c0 + 128, cin)].t().contiguous()) for c0 in range(0, cin, 128)]
+            dx = parts[0] if len(parts) == 1 else torch.cat(parts, -1)
         dw = db = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw = torch.zeros_like(w2)
