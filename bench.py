@@ -138,9 +138,10 @@ def cpu_pick_threads():
     return best
 
 
-def cpu_sample(threads, loop_iters=4, n=N_POINTS):
-    """One bounded CPU sample of the bench workload at B=1: everything before the loop (encoders, graphs,
-    correlation build) + `loop_iters` RAFT iterations, timed separately.  Returns (t_prepare, t_per_iteration)."""
+def cpu_sample(threads, loop_iters=ITERS, n=N_POINTS):
+    """One CPU sample of the bench workload at B=1: everything before the loop (encoders, graphs, correlation build) +
+    `loop_iters` RAFT iterations (all 32 by default: nothing is extrapolated), timed separately.
+    Returns (t_prepare, t_loop)."""
     from oracle import pvraft_oracle as O
     W = _cpu_weights()
     torch.set_num_threads(threads)
@@ -151,18 +152,38 @@ def cpu_sample(threads, loop_iters=4, n=N_POINTS):
         t1 = time.perf_counter()
         O.raft_loop(W, li, pc1, loop_iters, LEVELS, BASE_SCALE)
         t2 = time.perf_counter()
-    return t1 - t0, (t2 - t1) / loop_iters
+    return t1 - t0, t2 - t1
 
 
-def cpu_value(t_prep, t_iter):
-    """sample-iterations/s of a full forward (ITERS iterations) from the two measured parts."""
-    return ITERS / (t_prep + ITERS * t_iter)
+def gpu_reference_sample(dev, batch, iters):
+    """The reference FORMULATION on the same GPU: the oracle's op sequence (= the reference's own ATen ops, model/*.py) run by
+    torch eager on `dev`, fp32, TF32 off -- "the reference GPU build" of BASELINE.json's >= 10x target (the unmodified
+    reference cannot travel to the GPU box).  One warm-up at 2 iterations, one timed forward; returns seconds."""
+    from oracle import pvraft_oracle as O
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        W = {k: v.to(dev) for k, v in _cpu_weights().items()}
+        pc1, pc2 = [t.to(dev) for t in synthetic_clouds(batch, N_POINTS, 1234)]
+        with torch.no_grad():
+            O.rsf_forward(W, pc1, pc2, 2, LEVELS, BASE_SCALE, TRUNC_K)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            O.rsf_forward(W, pc1, pc2, iters, LEVELS, BASE_SCALE, TRUNC_K)
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        torch.cuda.empty_cache()
 
 
 def run_reference(a):
-    """`--impl reference`: the reference's CPU formulation (oracle port; the reference itself is pure PyTorch
-    and is not present on the GPU box) timed on the host cores, same metric / unit / config.  A step is the
-    bounded sample of cpu_sample(): the full pre-loop work + 4 of the 32 iterations at B=1, scaled to 32."""
+    """`--impl reference`: the reference's CPU formulation (oracle port; the reference itself is pure PyTorch and is not present on
+    the GPU box) timed on the host cores, same metric / unit / config.  A step is ONE full forward at B=1: the pre-loop work
+    and all 32 iterations are executed and timed (no extrapolation); steps stop early once ~200 s have been spent."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return None
@@ -170,40 +191,57 @@ def run_reference(a):
     warm = min(a.warmup, 1)
     for _ in range(warm):
         cpu_sample(threads, 1)
-    steps = max(1, a.steps)
-    t_prep = t_iter = 0.0
+    t_prep = t_loop = 0.0
     t_begin = time.perf_counter()
     done = 0
-    for _ in range(steps):
-        tp, ti = cpu_sample(threads)
+    for _ in range(max(1, a.steps)):
+        tp, tl = cpu_sample(threads)
         t_prep += tp
-        t_iter += ti
+        t_loop += tl
         done += 1
         if time.perf_counter() - t_begin > 200.0:      # keep the whole arm within a few minutes
             break
     t_prep /= done
-    t_iter /= done
-    value = cpu_value(t_prep, t_iter)
+    t_loop /= done
+    value = ITERS / (t_prep + t_loop)
     line = {
         'impl': 'reference', 'metric': 'raft_sample_iters_per_sec', 'value': value, 'unit': 'sample-iterations/s',
-        'n_gpus': a.gpus, 'steps': done, 'warmup': warm, 'ms_per_step': 1e3 * (t_prep + ITERS * t_iter),
+        'n_gpus': a.gpus, 'steps': done, 'warmup': warm, 'ms_per_step': 1e3 * (t_prep + t_loop),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(1, 1),
+        'config': workload_config(1, 1, ITERS),
         'cpu_baseline': {'value': value, 'unit': 'sample-iterations/s', 'cores': threads, 'kind': 'port',
-                         'sample': f'{done} x (pre-loop work + 4 of {ITERS} RAFT iterations) on B=1, N={N_POINTS}, scaled to '
-                                   f'{ITERS} iterations: t_prepare={t_prep:.2f} s, t_iteration={t_iter:.3f} s; torch CPU ops, '
+                         'sample': f'{done} full forwards at B=1, N={N_POINTS} (pre-loop work + all {ITERS} RAFT iterations, each '
+                                   f'measured: t_prepare={t_prep:.2f} s, t_loop={t_loop:.2f} s); torch CPU ops, '
                                    f'{threads} of {os.cpu_count()} host threads (fastest of a thread sweep)'},
         'e2e': {'value': value, 'unit': 'sample-iterations/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     return line
 
 
-def workload_config(batch_per_gpu, world):
+def workload_config(batch_per_gpu, world, iters, graph=False):
+    state_mb = batch_per_gpu * N_POINTS * TRUNC_K * 8 / 1e6
+    l2 = (f'per-iteration candidate state (B*N*K*8 B = {state_mb:.0f} MB/GPU) exceeds the 126 MB L2; no explicit flush' if state_mb > 126
+          else f'per-iteration candidate state is {state_mb:.0f} MB/GPU: L2-resident after the first iteration (labelled as such)')
     return {'workload': f'RSF.forward: N={N_POINTS} pts x2 clouds, truncate_k={TRUNC_K}, corr_levels={LEVELS}, '
-                        f'iters={ITERS}, batch {batch_per_gpu}/GPU, fp32 (BASELINE.json metric config; batch from configs[2])',
-            'global_batch': batch_per_gpu * world, 'points': N_POINTS, 'truncate_k': TRUNC_K, 'iters': ITERS,
-            'parallelism': f'batch-shard x{world} (no data-path collective)',
-            'l2_policy': 'per-iteration candidate state (B*N*K*8 B = 268 MB/GPU) exceeds the 126 MB L2; no explicit flush'}
+                        f'iters={iters}, batch {batch_per_gpu}/GPU, fp32 (BASELINE.json metric config; batch from configs[2])'
+                        + (', CUDA-graph replay' if graph else ''),
+            'global_batch': batch_per_gpu * world, 'points': N_POINTS, 'truncate_k': TRUNC_K, 'iters': iters,
+            'parallelism': f'batch-shard x{world} (no data-path collective)', 'l2_policy': l2}
+
+
+def lookup_traffic():
+    """dram__bytes_read+write per launch of the lookup kernel from the committed ncu capture -- only while that capture
+    belongs to the kernel source that is being timed (profiles/lookup_dram_bytes.json records the source's sha256)."""
+    import hashlib
+    path = os.path.join(ROOT, 'profiles', 'lookup_dram_bytes.json')
+    src = os.path.join(ROOT, 'pvraft_b200', 'csrc', 'corr_lookup.cu')
+    try:
+        rec = json.load(open(path))
+        if rec.get('source_sha256') == hashlib.sha256(open(src, 'rb').read()).hexdigest():
+            return rec.get('dram_bytes_per_launch')
+    except Exception:   # noqa: BLE001
+        pass
+    return None
 
 
 # --------------------------------------------------------------------------------------------------
@@ -215,9 +253,12 @@ def run_native(a):
     rank, world, local = D.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    B = a.batch
+    B, iters = a.batch, a.iters
     torch.manual_seed(0)
     model = RSF(make_args()).to(dev).eval()
+    if a.graph is not None:
+        model.use_cuda_graph = bool(a.graph)
+    graphed = model.use_cuda_graph if model.use_cuda_graph is not None else B <= 2
     pc1_h, pc2_h = synthetic_clouds(B, N_POINTS, 1234 + rank)
     pc1_h, pc2_h = pc1_h.pin_memory(), pc2_h.pin_memory()
     pc1, pc2 = pc1_h.to(dev), pc2_h.to(dev)
@@ -225,11 +266,11 @@ def run_native(a):
 
     def step_resident():
         with torch.no_grad():
-            return model([pc1, pc2], ITERS)[-1]
+            return model([pc1, pc2], iters)[-1]
 
     def step_e2e():
         with torch.no_grad():
-            flows = model([pc1_h.to(dev, non_blocking=True), pc2_h.to(dev, non_blocking=True)], ITERS)
+            flows = model([pc1_h.to(dev, non_blocking=True), pc2_h.to(dev, non_blocking=True)], iters)
             out_h.copy_(flows[-1], non_blocking=True)
         return flows[-1]
 
@@ -259,8 +300,8 @@ def run_native(a):
     step_e2e()
     ms_e2e, _, _ = timed(step_e2e, a.steps)
     gb = B * world
-    value = gb * ITERS * a.steps / (ms * 1e-3)
-    e2e = gb * ITERS * a.steps / (ms_e2e * 1e-3)
+    value = gb * iters * a.steps / (ms * 1e-3)
+    e2e = gb * iters * a.steps / (ms_e2e * 1e-3)
 
     # ---- dominant kernel: the fused correlation lookup, timed in situ with CUDA events ----------------
     lk_ms = []
@@ -275,10 +316,13 @@ def run_native(a):
         return r
 
     ops.corr_lookup = hooked
+    was_graph = model.use_cuda_graph
+    model.use_cuda_graph = False            # per-launch events need the eager launch sequence
     for _ in range(2):
         step_resident()
     torch.cuda.synchronize()
     ops.corr_lookup = orig
+    model.use_cuda_graph = was_graph
     durs = [s.elapsed_time(e) for s, e in lk_ms]
     lookup_ms = statistics.mean(durs)
     peaks, peak_kind = measured_peaks()
@@ -286,36 +330,133 @@ def run_native(a):
     achieved = alg / (lookup_ms * 1e-3) / 1e9
     roofline = {'kernel': 'k_corr_lookup (pvraft_corr_lookup_fwd)', 'bound': 'hbm', 'achieved': achieved,
                 'peak': peaks['hbm_gbs'], 'peak_kind': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)' if peak_kind == 'measured' else 'fallback',
-                'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': None,
+                'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': lookup_traffic(),
                 'alg_bytes_per_launch': alg, 'avg_launch_ms': lookup_ms, 'launches_timed': len(durs),
-                'share_of_step': lookup_ms * ITERS / (ms / a.steps)}
-    traffic_file = os.path.join(ROOT, 'profiles', 'lookup_dram_bytes.json')
-    if os.path.exists(traffic_file):
-        try:
-            roofline['traffic'] = json.load(open(traffic_file)).get('dram_bytes_per_launch')
-        except Exception:   # noqa: BLE001
-            pass
+                'share_of_step': lookup_ms * iters / (ms / a.steps)}
 
     if rank != 0:
         return None
-    cpu = None
+    cpu = gpu_ref = None
     if world == 1 and not a.no_cpu:
         threads = cpu_pick_threads()
-        tp, ti = cpu_sample(threads)
-        cpu = {'value': cpu_value(tp, ti), 'unit': 'sample-iterations/s', 'cores': threads, 'kind': 'port',
-               'sample': f'pre-loop work + 4 of {ITERS} RAFT iterations on B=1, N={N_POINTS}, scaled to {ITERS} iterations '
-                         f'(t_prepare={tp:.2f} s, t_iteration={ti:.3f} s; oracle port of the reference, torch CPU ops, '
+        tp, tl = cpu_sample(threads)
+        cpu = {'value': ITERS / (tp + tl), 'unit': 'sample-iterations/s', 'cores': threads, 'kind': 'port',
+               'sample': f'one full forward at B=1, N={N_POINTS}: pre-loop work + all {ITERS} RAFT iterations, measured '
+                         f'(t_prepare={tp:.2f} s, t_loop={tl:.2f} s; oracle port of the reference, torch CPU ops, '
                          f'{threads} of {os.cpu_count()} host threads)'}
+    if world == 1 and not a.no_gpu_ref:
+        try:
+            t_ref = gpu_reference_sample(dev, B, iters)
+            gpu_ref = {'value': B * iters / t_ref, 'unit': 'sample-iterations/s', 'ms_per_step': 1e3 * t_ref,
+                       'kind': "the reference's own op sequence (oracle port of model/*.py) in torch eager on this GPU, fp32, TF32 off, "
+                               f'batch {B}, {iters} iterations, one timed forward after a warm-up',
+                       'speedup': value / (B * iters / t_ref)}
+        except Exception as e:   # noqa: BLE001  (out of memory on a smaller device: report, do not fail the bench)
+            gpu_ref = {'unavailable': f'{type(e).__name__}: {e}'[:200]}
     line = {
         'metric': 'raft_sample_iters_per_sec', 'value': value, 'unit': 'sample-iterations/s', 'n_gpus': world,
         'steps': a.steps, 'warmup': max(a.warmup, 3), 'ms_per_step': ms / a.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(B, world),
+        'config': workload_config(B, world, iters, graphed),
         'e2e': {'value': e2e, 'unit': 'sample-iterations/s', 'h2d_bytes_per_step': 2 * B * N_POINTS * 3 * 4 * world,
                 'd2h_bytes_per_step': B * N_POINTS * 3 * 4 * world, 'ms_per_step': ms_e2e / a.steps},
-        'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu,
+        'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'gpu_reference': gpu_ref,
     }
     return line
+
+
+# --------------------------------------------------------------------------------------------------
+# training step (BASELINE.json configs[3]): fwd + bwd + Adam, batch sharded over the ranks, ONE gradient all-reduce
+# --------------------------------------------------------------------------------------------------
+def run_train(a):
+    import torch.distributed as dist
+    from pvraft_b200 import RSF, ops
+    from pvraft_b200 import dist as D
+    rank, world, local = D.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    B, iters = a.batch, a.iters
+    torch.manual_seed(0)
+    model = RSF(make_args()).to(dev).train()
+    wrapped = D.ddp(model, local)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)                       # tools/engine.py:57
+    pc1_h, pc2_h = synthetic_clouds(B, N_POINTS, 1234 + rank)
+    pc1_h, pc2_h = pc1_h.pin_memory(), pc2_h.pin_memory()
+    pc1, pc2 = pc1_h.to(dev), pc2_h.to(dev)
+    loss_h = torch.empty(1).pin_memory()
+
+    def loss_fn(flows, gt, gamma=0.8):                                        # tools/loss.py:4-13 (all-ones mask)
+        n = len(flows)
+        return sum(gamma ** (n - i - 1) * (flows[i] - gt).abs().sum(-1).mean() for i in range(n))
+
+    def step(x1, x2):
+        opt.zero_grad(set_to_none=True)
+        flows = wrapped([x1, x2], num_iters=iters)
+        loss = loss_fn(flows, x2 - x1)
+        loss.backward()                                                       # DDP: the 750 KiB gradient all-reduce happens here
+        opt.step()
+        return loss
+
+    def step_resident():
+        return step(pc1, pc2)
+
+    def step_e2e():
+        loss = step(pc1_h.to(dev, non_blocking=True), pc2_h.to(dev, non_blocking=True))
+        loss_h.copy_(loss.detach().reshape(1), non_blocking=True)
+        return loss
+
+    def timed(fn, steps):
+        D.barrier()
+        torch.cuda.synchronize()
+        l0 = ops.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        D.barrier()
+        return D.max_over_ranks(e0.elapsed_time(e1), dev), ops.launch_count - l0
+
+    for _ in range(max(a.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches = timed(step_resident, a.steps)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, _ = timed(step_e2e, a.steps)
+    # the collective alone: one all-reduce of a gradient-sized fp32 buffer
+    nparam = sum(p.numel() for p in model.parameters())
+    coll = {'bytes': nparam * 4, 'ranks': world, 'standalone_us': None}
+    if world > 1:
+        buf = torch.zeros(nparam, device=dev)
+        for _ in range(5):
+            dist.all_reduce(buf)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            dist.all_reduce(buf)
+        e1.record()
+        torch.cuda.synchronize()
+        coll['standalone_us'] = D.max_over_ranks(e0.elapsed_time(e1) / 20 * 1e3, dev)
+        coll['share_of_step'] = coll['standalone_us'] * 1e-3 / (ms / a.steps)
+    if rank != 0:
+        return None
+    gb = B * world
+    return {
+        'metric': 'raft_train_sample_iters_per_sec', 'value': gb * iters * a.steps / (ms * 1e-3), 'unit': 'sample-iterations/s',
+        'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3), 'ms_per_step': ms / a.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'training step (forward + backward + Adam) of RSF: N={N_POINTS} pts x2 clouds, truncate_k={TRUNC_K}, '
+                               f'iters={iters}, batch {B}/GPU, fp32 (BASELINE.json configs[3])', 'global_batch': gb, 'points': N_POINTS,
+                   'truncate_k': TRUNC_K, 'iters': iters,
+                   'parallelism': f'DDP batch-shard x{world}: one gradient all-reduce of {nparam * 4} B per step (NCCL)'},
+        'e2e': {'value': gb * iters * a.steps / (ms_e2e * 1e-3), 'unit': 'sample-iterations/s',
+                'h2d_bytes_per_step': 2 * B * N_POINTS * 3 * 4 * world, 'd2h_bytes_per_step': 4 * world, 'ms_per_step': ms_e2e / a.steps},
+        'gpu_launches': launches, 'clocks': clocks, 'collective': coll,
+    }
 
 
 class _QuietStdout:
@@ -340,11 +481,22 @@ def main():
     ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', choices=['native', 'reference'], default='native')
-    ap.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='samples per GPU')
+    ap.add_argument('--mode', choices=['infer', 'train'], default='infer', help='train = BASELINE configs[3] (fwd+bwd+Adam, DDP)')
+    ap.add_argument('--batch', type=int, default=None, help='samples per GPU (default 8; 2 in train mode)')
+    ap.add_argument('--iters', type=int, default=None, help='RAFT iterations (default 32; 8 in train mode)')
+    ap.add_argument('--graph', type=int, default=None, help='1/0 force CUDA-graph replay on/off (default: automatic for batch <= 2)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-gpu-ref', action='store_true', help='skip the gpu_reference leg')
     a = ap.parse_args()
+    if a.batch is None:
+        a.batch = 2 if a.mode == 'train' else BATCH_PER_GPU
+    if a.iters is None:
+        a.iters = 8 if a.mode == 'train' else ITERS
     with _QuietStdout():
-        line = run_reference(a) if a.impl == 'reference' else run_native(a)
+        if a.impl == 'reference':
+            line = run_reference(a)
+        else:
+            line = run_train(a) if a.mode == 'train' else run_native(a)
     if line is not None:
         print(json.dumps(line), flush=True)
     if torch.distributed.is_available() and torch.distributed.is_initialized():

@@ -22,18 +22,26 @@ from .update import UpdateBlock
 def _records_grad(module):
     """True when the caller differentiates through this forward (tools/engine.py:140-143): the training path of train.py runs;
     otherwise (torch.no_grad(), or nothing requires grad) the fused inference kernels do."""
-    return torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())
+    if not torch.is_grad_enabled():
+        return False
+    for m in module.modules():
+        # nn.DataParallel replicas keep their (non-leaf) parameter copies in `_former_parameters`; `.parameters()` is empty there
+        for t in list(m._parameters.values()) + list(getattr(m, '_former_parameters', {}).values()):
+            if t is not None and t.requires_grad:
+                return True
+    return False
 
 
 class _RaftBase(nn.Module):
     # CUDA-graph replay of the whole forward (encoders, correlation build, all iterations): the eager path costs ~28 us of
     # host time per launch (python + ctypes + tensor-map encodes), which bounds small batches (B <= 2: ~0.5 ms per
-    # iteration).  Opt-in: `model.use_cuda_graph = True` or PVRAFT_CUDA_GRAPH=1.  One graph per (B, N, num_iters); inputs are
+    # iteration).  `use_cuda_graph = None` (default) replays graphs for inference batches of at most 2 samples, True / False
+    # (or PVRAFT_CUDA_GRAPH=1 / 0) force it on / off.  One graph per (B, N, num_iters); inputs are
     # copied into the graph's static buffers, outputs are returned as copies.  The kernels read DERIVED copies of the weights
     # (tf32 hi/lo splits, folded products, bias sums, PReLU slopes known to the host) that are fixed at capture time, so a
     # graph is only valid for the parameter values it was captured with: every entry records (version, data_ptr) of all
     # parameters and is re-captured when any of them changed (optimizer step, load_state_dict, .to()).
-    use_cuda_graph = os.environ.get('PVRAFT_CUDA_GRAPH', '0') == '1'
+    use_cuda_graph = {'1': True, '0': False}.get(os.environ.get('PVRAFT_CUDA_GRAPH', ''), None)
     # Morton-order the first cloud internally (see _encode).  Off by default: in isolation the edge kernel gains 18 %
     # (101 -> 83 us), but per forward it is a wash at B = 8 (20.87 vs 20.88 ms with the order from the library's grid sort,
     # 21.34 with a torch-side sort).
@@ -45,7 +53,7 @@ class _RaftBase(nn.Module):
     def _graphed(self, p, num_iters):
         xyz1, xyz2 = p[0].detach().contiguous().float(), p[1].detach().contiguous().float()
         graphs = self.__dict__.setdefault('_graphs', {})
-        key = (tuple(xyz1.shape), xyz1.device, int(num_iters))
+        key = (tuple(xyz1.shape), xyz1.device, int(num_iters), bool(self.sort_points))
         entry = graphs.get(key)
         stamp = tuple((q._version, q.data_ptr()) for q in self.parameters())
         if entry is not None and entry[3] != stamp:
@@ -61,13 +69,15 @@ class _RaftBase(nn.Module):
                     self._forward_impl(static_in, num_iters)
             torch.cuda.current_stream(xyz1.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
+            l0 = ops.launch_count
             with torch.cuda.graph(graph):
                 static_out = self._forward_impl(static_in, num_iters)
-            entry = graphs[key] = (graph, static_in, static_out, stamp)
-        graph, static_in, static_out, _ = entry
+            entry = graphs[key] = (graph, static_in, static_out, stamp, ops.launch_count - l0)
+        graph, static_in, static_out, _, n_kernels = entry
         static_in[0].copy_(xyz1)
         static_in[1].copy_(xyz2)
         graph.replay()
+        ops.launch_count += n_kernels            # the library's kernels inside the replayed graph
         return static_out.clone() if torch.is_tensor(static_out) else [t.clone() for t in static_out]
 
     def forward(self, p, num_iters=12):
@@ -76,7 +86,10 @@ class _RaftBase(nn.Module):
         with torch.cuda.device(p[0].device):        # the library launches on the current device
             if _records_grad(self):
                 return self._forward_train(p, num_iters)
-            if self.use_cuda_graph:
+            graph = self.use_cuda_graph
+            if graph is None:    # automatic: small inference batches are host-bound (not inside an nn.DataParallel replica thread)
+                graph = p[0].shape[0] <= 2 and not getattr(self, '_is_replica', False)
+            if graph:
                 return self._graphed(p, num_iters)
             return self._forward_impl(p, num_iters)
 

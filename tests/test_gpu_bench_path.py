@@ -161,9 +161,13 @@ def test_config2_build_matches_oracle_state(dev, config2):
 
 def _free_running(m, pc1, pc2, iters, dev):
     with torch.no_grad():
-        own = m([pc1.to(dev), pc2.to(dev)], iters)
-        with oracle_adjacency():
-            common = m([pc1.to(dev), pc2.to(dev)], iters)
+        own = m([pc1.to(dev), pc2.to(dev)], iters)            # as shipped (CUDA-graph replay for batches <= 2)
+        auto, m.use_cuda_graph = m.use_cuda_graph, False      # the oracle's adjacency is computed on the host: not capturable
+        try:
+            with oracle_adjacency():
+                common = m([pc1.to(dev), pc2.to(dev)], iters)
+        finally:
+            m.use_cuda_graph = auto
     return own, common
 
 

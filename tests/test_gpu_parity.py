@@ -480,6 +480,7 @@ def test_cuda_graph_replay_matches_eager(dev):
     m = RSF(args).to(dev).eval()
     clouds = [O.synthetic_clouds(2, 1024, seed=s) for s in (5, 6)]
     with torch.no_grad():
+        m.use_cuda_graph = False
         eager = [m([a.to(dev), b.to(dev)], 3)[-1].clone() for a, b in clouds]
         m.use_cuda_graph = True
         graphed = [m([a.to(dev), b.to(dev)], 3)[-1].clone() for a, b in clouds]

@@ -147,6 +147,42 @@ def test_two_rank_gloo_shard_gather_and_timing():
         assert ok and t == 2.0 and s == 5.0
 
 
+def _grad_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from pvraft_b200 import dist as D
+    r, w, _ = D.init_from_env(backend='gloo')
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.GroupNorm(1, 5), torch.nn.Linear(5, 3))   # per-sample norm, as the model
+    x = torch.randn(8, 6, generator=torch.Generator().manual_seed(1))
+    y = torch.randn(8, 3, generator=torch.Generator().manual_seed(2))
+    lo, hi = D.shard_range(8, r, w)
+    (net(x[lo:hi]) - y[lo:hi]).abs().mean().backward()          # masked-mean loss of the rank's shard (tools/loss.py:34-38)
+    nbytes = D.allreduce_gradients(net.parameters())
+    got = [p.grad.clone() for p in net.parameters()]
+    net.zero_grad()
+    (net(x) - y).abs().mean().backward()                        # the same step on the concatenated batch
+    want = [p.grad for p in net.parameters()]
+    out[rank] = (all(torch.allclose(a, b, rtol=1e-5, atol=1e-7) for a, b in zip(got, want)), nbytes)
+    wrapped = D.ddp(net)                                        # the DDP wrapper gives the same averaged gradients
+    wrapped.zero_grad()
+    (wrapped(x[lo:hi]) - y[lo:hi]).abs().mean().backward()
+    out[rank] = out[rank] + (all(torch.allclose(p.grad, b, rtol=1e-5, atol=1e-7) for p, b in zip(net.parameters(), want)),)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_allreduce_equals_the_full_batch():
+    """SURVEY 8c item 5 (host-side logic on CPU): per-rank shard gradients, one all-reduce (sum -> mean), == the gradient of
+    the concatenated batch, because every normalisation is per sample and the loss is a mean over equal shards."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_grad_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for r in range(world):
+        ok, nbytes, ok_ddp = out[r]
+        assert ok and ok_ddp and nbytes == 4 * (6 * 5 + 5 + 5 + 5 + 5 * 3 + 3)
+
+
 def test_division_by_constant_sequence_is_exact():
     """k_corr_gemm divides by sqrt(C) with q0 = x*r, q = q0 + (x - q0*s)*r, r = RN(1/s) (csrc/corr_gemm.cu: div_by_const).
     Emulated here in numpy (an fp32 FMA = the double-precision product-sum rounded once to fp32): bit-identical to the true
