@@ -409,6 +409,17 @@ PVRAFT_API int pvraft_corr_lookup_bwd(const int32_t* corr_idx, const float* xyz2
 PVRAFT_API int pvraft_corr_init_bwd(const float* g, const int32_t* idx, const float* fmap1, const float* fmap2, int B, int N, int C, int K,
                          float* d_fmap1, float* d_fmap2, void* stream);
 
+/* Training extras on the device.  est, gt [points,3]; mask [points] (> 0 = valid) or NULL.
+ *   pvraft_flow_metrics_fwd: acc[6] double, ZEROED by the caller, accumulates over the valid points
+ *       [0] sum |ex|+|ey|+|ez|  (tools/loss.py:34-38: loss = acc[0] / (3 acc[1]))      [1] number of valid points
+ *       [2] sum ||e||           (tools/metric.py:24-29: EPE = acc[2] / acc[1])
+ *       [3],[4],[5] points with (epe<.05 or rel<.05), (epe<.1 or rel<.1), (epe>.3 or rel>.1), rel = epe/(||gt||+1e-4)  (metric.py:66-77)
+ *   pvraft_flow_l1_bwd: d_est = g[0] * weight * sign(est - gt) / (3 acc[1]) on valid points, 0 elsewhere; g is a DEVICE scalar
+ *       (the upstream gradient), acc the forward's accumulator: no host synchronisation between forward and backward. */
+PVRAFT_API int pvraft_flow_metrics_fwd(const float* est, const float* gt, const float* mask, int64_t points, double* acc, void* stream);
+PVRAFT_API int pvraft_flow_l1_bwd(const float* est, const float* gt, const float* mask, int64_t points, const double* acc, const float* g,
+                       float weight, float* d_est, void* stream);
+
 /* sizeof() of the argument structs as compiled into the library (0 = linear, 1 = corrfeat, 2 = gru,
  * 3 = flowout, 4 = tc_linear; -1 otherwise): lets a foreign-language binding verify its struct layout at load time. */
 PVRAFT_API int pvraft_sizeof(int which);

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libpvraft_b200.so')
-SOURCES = ['capi.cu', 'corr_gemm.cu', 'corr_lookup.cu', 'corr_topk.cu', 'knn.cu', 'knn_branch.cu', 'pointmlp.cu', 'setconv_edge.cu', 'tc_linear.cu', 'train.cu']
+SOURCES = ['capi.cu', 'flow_metrics.cu', 'corr_gemm.cu', 'corr_lookup.cu', 'corr_topk.cu', 'knn.cu', 'knn_branch.cu', 'pointmlp.cu', 'setconv_edge.cu', 'tc_linear.cu', 'train.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
 

@@ -294,3 +294,52 @@ def test_training_steps_like_the_engine(dev):
         Wn = {kk: v.detach().cpu() for kk, v in m.state_dict().items()}
         want = O.rsf_forward(Wn, pc1.cpu(), pc2.cpu(), 2, 3, 0.25, 64)
     assert float((ev[-1].cpu() - want[-1]).abs().mean()) < 1e-2 * float(want[-1].abs().mean())
+
+
+def test_device_side_loss_and_metrics(dev):
+    """pvraft_b200.loss (and the tools/loss.py, tools/metric.py drop-ins) against the reference formulas restated in torch / numpy
+    (tools/loss.py:4-40, tools/metric.py:6-79), forward and backward, with a partial mask."""
+    import numpy as np
+    from tools.loss import sequence_loss as seq_loss
+    from tools.metric import compute_epe, compute_epe_train
+    g = torch.Generator().manual_seed(0)
+    b, n = 2, 700
+    mask = (torch.rand(b, n, 1, generator=g) > 0.3).float()
+    gt = torch.randn(b, n, 3, generator=g) * 0.5
+    ests = [gt + torch.randn(b, n, 3, generator=g) * s for s in (0.4, 0.2, 0.05)]
+    batch = {'ground_truth': [mask.to(dev), gt.to(dev)]}
+    xs = [leaf(e, dev) for e in ests]
+    loss = seq_loss(xs, batch, gamma=0.8)
+    loss.backward()
+    xr = [leaf(e) for e in ests]
+    want = 0
+    for i, e in enumerate(xr):
+        err = (e - gt)[mask[..., 0] > 0]
+        want = want + 0.8 ** (2 - i) * torch.mean(torch.abs(err))
+    want.backward()
+    assert abs(float(loss) - float(want)) < 1e-6 * abs(float(want))
+    for a, r in zip(xs, xr):
+        assert rel_err(a.grad.cpu(), r.grad) < 1e-6
+    epe = compute_epe_train(xs[-1].detach(), batch)
+    assert epe.is_cuda and epe.dim() == 0
+    m = mask.numpy()[..., 0]
+    sf_gt, sf_pred = gt.numpy()[m > 0], ests[-1].numpy()[m > 0]
+    l2 = np.linalg.norm(sf_gt - sf_pred, axis=-1)
+    rel = l2 / (np.linalg.norm(sf_gt, axis=-1) + 1e-4)
+    ref = (l2.mean(), np.logical_or(l2 < 0.05, rel < 0.05).mean(), np.logical_or(l2 < 0.1, rel < 0.1).mean(),
+           np.logical_or(l2 > 0.3, rel > 0.1).mean())
+    assert abs(float(epe) - ref[0]) < 1e-6
+    got = compute_epe(xs[-1].detach(), batch)
+    assert all(abs(a - float(r)) < 2e-3 for a, r in zip(got, ref)), (got, ref)       # threshold counts may differ by a point at the edge
+
+
+def test_batch_pins_once_and_moves_with_one_copy(dev):
+    from pvraft_b200.data import Batch
+    g = torch.Generator().manual_seed(2)
+    items = [{'sequence': [torch.rand(1, 64, 3, generator=g), torch.rand(1, 64, 3, generator=g)],
+              'ground_truth': [torch.ones(1, 64, 1), torch.randn(1, 64, 3, generator=g)]} for _ in range(2)]
+    want = [torch.cat([it['sequence'][0] for it in items], 0), torch.cat([it['ground_truth'][1] for it in items], 0)]
+    bt = Batch(items).pin_memory()
+    assert bt['sequence'][0].is_pinned()
+    bt = bt.to(dev)
+    assert bt['sequence'][0].is_cuda and torch.equal(bt['sequence'][0].cpu(), want[0]) and torch.equal(bt['ground_truth'][1].cpu(), want[1])

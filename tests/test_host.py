@@ -251,3 +251,35 @@ def test_weight_folds_equal_the_unfused_layers():
     w, b = fold_corr_motion(w_cc, b_cc, w_out, b_out, w_kout, b_kout)
     got = torch.cat([a, k], 1) @ w.double().T + b.double()
     assert float((got - want).abs().max() / want.abs().max()) < 1e-6
+
+
+def _items(b, n, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return [{'sequence': [torch.rand(1, n, 3, generator=g), torch.rand(1, n, 3, generator=g)],
+             'ground_truth': [(torch.rand(1, n, 1, generator=g) > 0.2).float(), torch.randn(1, n, 3, generator=g)]} for _ in range(b)]
+
+
+def test_batch_collate_matches_the_reference_class():
+    """pvraft_b200.data.Batch against datasets/generic.py:6-66 (the reference class itself when its tree is present, loaded by
+    file path because the HuggingFace `datasets` package shadows the namespace package; its documented behaviour otherwise)."""
+    from pvraft_b200.data import Batch, subsample
+    items = _items(3, 50)
+    mine = Batch(items)
+    ref_path = '/root/reference/datasets/generic.py'
+    if os.path.exists(ref_path):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location('ref_generic', ref_path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        ref = mod.Batch(items).data
+    else:
+        ref = {k: [torch.cat([it[k][i] for it in items], 0) for i in range(2)] for k in ('sequence', 'ground_truth')}
+    for key in ('sequence', 'ground_truth'):
+        for a, b in zip(mine[key], ref[key]):
+            assert a.shape == b.shape and torch.equal(a, b)
+    moved = mine.to('cpu')
+    assert moved is mine and torch.equal(mine['sequence'][1], ref['sequence'][1])
+    assert mine['sequence'][0].untyped_storage().data_ptr() == mine['ground_truth'][1].untyped_storage().data_ptr()   # one buffer
+    pts = torch.arange(300.).view(100, 3)
+    sub, lab = subsample(pts, 40, generator=torch.Generator().manual_seed(1), extra=(torch.arange(100),))
+    assert sub.shape == (40, 3) and torch.equal(sub, pts[lab]) and len(set(lab.tolist())) == 40
