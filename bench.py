@@ -28,9 +28,12 @@ N_POINTS, TRUNC_K, ITERS, LEVELS, BASE_SCALE = 8192, 512, 32, 3, 0.25
 BATCH_PER_GPU = 8        # 8 x 32 MiB of (corr, index) state = 268 MB > the 126 MB L2: the lookup streams from HBM
 
 
-def alg_bytes_lookup(n, k, levels=LEVELS):
+def alg_bytes_lookup(n, k, levels=LEVELS, bf16=False):
     """ALGORITHMIC bytes of one sample-iteration of the lookup kernel:
-    K*(4 B corr + 4 B index) + 12 B coords in, levels*27*4 B voxel means + 32*16 B kNN vectors out."""
+    fp32: K*(4 B corr + 4 B index) + 12 B coords in, levels*27*4 B voxel means + 32*16 B kNN vectors out = N*4944;
+    bf16 mode: K*(2 + 2) + 12 in, levels*27*2 + 32*8 out = N*2478."""
+    if bf16:
+        return n * (k * 4 + 12 + levels * 27 * 2 + 32 * 8)
     return n * (k * 8 + 12 + levels * 27 * 4 + 32 * 16)
 
 
@@ -218,12 +221,14 @@ def run_reference(a):
     return line
 
 
-def workload_config(batch_per_gpu, world, iters, graph=False):
-    state_mb = batch_per_gpu * N_POINTS * TRUNC_K * 8 / 1e6
-    l2 = (f'per-iteration candidate state (B*N*K*8 B = {state_mb:.0f} MB/GPU) exceeds the 126 MB L2; no explicit flush' if state_mb > 126
+def workload_config(batch_per_gpu, world, iters, graph=False, refine=False, dtype='f32'):
+    state_mb = batch_per_gpu * N_POINTS * TRUNC_K * (4 if dtype == 'bf16' else 8) / 1e6
+    l2 = (f'per-iteration candidate state ({state_mb:.0f} MB/GPU) exceeds the 126 MB L2; no explicit flush' if state_mb > 126
           else f'per-iteration candidate state is {state_mb:.0f} MB/GPU: L2-resident after the first iteration (labelled as such)')
-    return {'workload': f'RSF.forward: N={N_POINTS} pts x2 clouds, truncate_k={TRUNC_K}, corr_levels={LEVELS}, '
-                        f'iters={iters}, batch {batch_per_gpu}/GPU, fp32 (BASELINE.json metric config; batch from configs[2])'
+    mode = ('bf16 correlation state + uint16 ids, fp32 coordinates / index math / layers (BASELINE.json configs[2])' if dtype == 'bf16'
+            else 'fp32 (BASELINE.json metric config; batch from configs[2])')
+    return {'workload': f'{"RSF_refine" if refine else "RSF"}.forward: N={N_POINTS} pts x2 clouds, truncate_k={TRUNC_K}, corr_levels={LEVELS}, '
+                        f'iters={iters}, batch {batch_per_gpu}/GPU, {mode}'
                         + (', CUDA-graph replay' if graph else ''),
             'global_batch': batch_per_gpu * world, 'points': N_POINTS, 'truncate_k': TRUNC_K, 'iters': iters,
             'parallelism': f'batch-shard x{world} (no data-path collective)', 'l2_policy': l2}
@@ -248,14 +253,16 @@ def lookup_traffic():
 # native arm
 # --------------------------------------------------------------------------------------------------
 def run_native(a):
-    from pvraft_b200 import RSF, ops
+    from pvraft_b200 import RSF, RSF_refine, ops
     from pvraft_b200 import dist as D
     rank, world, local = D.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     B, iters = a.batch, a.iters
     torch.manual_seed(0)
-    model = RSF(make_args()).to(dev).eval()
+    model = (RSF_refine if a.refine else RSF)(make_args()).to(dev).eval()
+    model.set_precision('bf16' if a.dtype == 'bf16' else 'fp32')
+    last = (lambda out: out) if a.refine else (lambda out: out[-1])
     if a.graph is not None:
         model.use_cuda_graph = bool(a.graph)
     graphed = model.use_cuda_graph if model.use_cuda_graph is not None else B <= 2
@@ -266,13 +273,13 @@ def run_native(a):
 
     def step_resident():
         with torch.no_grad():
-            return model([pc1, pc2], iters)[-1]
+            return last(model([pc1, pc2], iters))
 
     def step_e2e():
         with torch.no_grad():
-            flows = model([pc1_h.to(dev, non_blocking=True), pc2_h.to(dev, non_blocking=True)], iters)
-            out_h.copy_(flows[-1], non_blocking=True)
-        return flows[-1]
+            flow = last(model([pc1_h.to(dev, non_blocking=True), pc2_h.to(dev, non_blocking=True)], iters))
+            out_h.copy_(flow, non_blocking=True)
+        return flow
 
     def timed(fn, steps, sample_clocks=False):
         D.barrier()
@@ -326,11 +333,11 @@ def run_native(a):
     durs = [s.elapsed_time(e) for s, e in lk_ms]
     lookup_ms = statistics.mean(durs)
     peaks, peak_kind = measured_peaks()
-    alg = alg_bytes_lookup(N_POINTS, TRUNC_K) * B
+    alg = alg_bytes_lookup(N_POINTS, TRUNC_K, bf16=a.dtype == 'bf16') * B
     achieved = alg / (lookup_ms * 1e-3) / 1e9
-    roofline = {'kernel': 'k_corr_lookup (pvraft_corr_lookup_fwd)', 'bound': 'hbm', 'achieved': achieved,
+    roofline = {'kernel': 'k_corr_lookup (pvraft_corr_lookup_bf16_fwd)' if a.dtype == 'bf16' else 'k_corr_lookup (pvraft_corr_lookup_fwd)', 'bound': 'hbm', 'achieved': achieved,
                 'peak': peaks['hbm_gbs'], 'peak_kind': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)' if peak_kind == 'measured' else 'fallback',
-                'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': lookup_traffic(),
+                'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': lookup_traffic() if a.dtype == 'f32' else None,
                 'alg_bytes_per_launch': alg, 'avg_launch_ms': lookup_ms, 'launches_timed': len(durs),
                 'share_of_step': lookup_ms * iters / (ms / a.steps)}
 
@@ -344,7 +351,7 @@ def run_native(a):
                'sample': f'one full forward at B=1, N={N_POINTS}: pre-loop work + all {ITERS} RAFT iterations, measured '
                          f'(t_prepare={tp:.2f} s, t_loop={tl:.2f} s; oracle port of the reference, torch CPU ops, '
                          f'{threads} of {os.cpu_count()} host threads)'}
-    if world == 1 and not a.no_gpu_ref:
+    if world == 1 and not a.no_gpu_ref and not a.refine:
         try:
             t_ref = gpu_reference_sample(dev, B, iters)
             gpu_ref = {'value': B * iters / t_ref, 'unit': 'sample-iterations/s', 'ms_per_step': 1e3 * t_ref,
@@ -356,8 +363,8 @@ def run_native(a):
     line = {
         'metric': 'raft_sample_iters_per_sec', 'value': value, 'unit': 'sample-iterations/s', 'n_gpus': world,
         'steps': a.steps, 'warmup': max(a.warmup, 3), 'ms_per_step': ms / a.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(B, world, iters, graphed),
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': a.dtype, 'data': 'synthetic',
+        'config': workload_config(B, world, iters, graphed, a.refine, a.dtype),
         'e2e': {'value': e2e, 'unit': 'sample-iterations/s', 'h2d_bytes_per_step': 2 * B * N_POINTS * 3 * 4 * world,
                 'd2h_bytes_per_step': B * N_POINTS * 3 * 4 * world, 'ms_per_step': ms_e2e / a.steps},
         'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'gpu_reference': gpu_ref,
@@ -485,6 +492,8 @@ def main():
     ap.add_argument('--batch', type=int, default=None, help='samples per GPU (default 8; 2 in train mode)')
     ap.add_argument('--iters', type=int, default=None, help='RAFT iterations (default 32; 8 in train mode)')
     ap.add_argument('--graph', type=int, default=None, help='1/0 force CUDA-graph replay on/off (default: automatic for batch <= 2)')
+    ap.add_argument('--dtype', choices=['f32', 'bf16'], default='f32', help='bf16 = reduced-precision correlation state (configs[2])')
+    ap.add_argument('--refine', action='store_true', help='RSF_refine instead of RSF (configs[2])')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-gpu-ref', action='store_true', help='skip the gpu_reference leg')
     a = ap.parse_args()

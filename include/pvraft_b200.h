@@ -106,6 +106,16 @@ PVRAFT_API int pvraft_corr_reorder(const float* val_in, const int32_t* idx_in, i
  *                                pre-test, the compaction and the per-level cell codes); test hook, NULL in production
  * K in {32,64,128,256,512,1024}; 1 <= levels <= 4; knn fixed at 32.
  * --------------------------------------------------------------------------------------------- */
+/* The same lookup on the reduced-precision state of BASELINE.json configs[2] ("bf16 mode"): correlation values as
+ * bf16 bit patterns and candidate ids as uint16 (N <= 65536) -- 4 B instead of 8 B per candidate and iteration.  Index math
+ * (coordinates, cells, kNN distances) stays fp32 and bit-exact; values are widened to fp32 exactly and accumulated in fp32, so
+ * the outputs equal pvraft_corr_lookup_fwd on the bf16-rounded correlations.  K in {128,256,512,1024}.
+ * pvraft_corr_state_pack_bf16 converts a reordered fp32/int32 state (round to nearest even). */
+PVRAFT_API int pvraft_corr_lookup_bf16_fwd(const uint16_t* corr_val_bf16, const uint16_t* corr_idx_u16, const float* xyz2_pad,
+                                const float* coords, int B, int N, int K, int levels, float base_scale, float* vox, int vox_ld,
+                                float* knn_sel, int32_t* knn_slot, double* moments, int8_t* dbg_cube, void* stream);
+PVRAFT_API int pvraft_corr_state_pack_bf16(const float* val, const int32_t* idx, int64_t n, uint16_t* val_out, uint16_t* idx_out, void* stream);
+
 /* xyz [rows,3] -> out [rows,4] = (x,y,z,0): the gather table of the lookup kernel (one 128-bit load per candidate). */
 PVRAFT_API int pvraft_xyz_pad_fwd(const float* xyz, int64_t rows, float* out, void* stream);
 PVRAFT_API int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr_idx, const float* xyz2_pad, const float* coords,

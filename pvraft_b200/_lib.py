@@ -74,6 +74,9 @@ _SIGNATURES = {
     'pvraft_xyz_pad_fwd': (C.c_int, [VP, C.c_int64, VP, VP]),
     'pvraft_corr_lookup_fwd': (C.c_int, [VP, VP, VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                          VP, C.c_int, VP, VP, VP, VP, VP]),
+    'pvraft_corr_lookup_bf16_fwd': (C.c_int, [VP, VP, VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                              VP, C.c_int, VP, VP, VP, VP, VP]),
+    'pvraft_corr_state_pack_bf16': (C.c_int, [VP, VP, C.c_int64, VP, VP, VP]),
     'pvraft_linear_fwd': (C.c_int, [C.POINTER(LinearArgs), VP]),
     'pvraft_tc_linear_fwd': (C.c_int, [C.POINTER(TcLinearArgs), VP]),
     'pvraft_tc_weight_split': (C.c_int, [VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, VP, VP, VP]),

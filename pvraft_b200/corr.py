@@ -56,6 +56,9 @@ class CorrBlock(nn.Module):
         self.knn_out = nn.Conv1d(64, 64, 1)
         self.corr_val = None     # [B,N,K] f32 correlation of the kept candidates (bank-aware order, see ops.corr_reorder)
         self.corr_idx = None     # [B,N,K] int32 candidate ids (rows of xyz2), same order
+        # torch.bfloat16 = the reduced-precision state of BASELINE configs[2] (bf16 values + uint16 ids, 4 B per candidate and
+        # iteration; index math stays fp32): inference only, set through RSF.set_precision('bf16')
+        self.state_dtype = torch.float32
         self._xyz2 = None
         self._xyz2p = None   # [B,N,4] (x,y,z,0): the lookup kernel's gather table
 
@@ -94,32 +97,42 @@ class CorrBlock(nn.Module):
             raise ValueError(f'truncate_k={self.truncate_k} exceeds the number of points {n_p}')
         corr = self.calculate_corr_pm(fmap1_pm.contiguous(), fmap2_pm.contiguous())   # tcgen05, 3xTF32 (fp32-accurate)
         val, idx = ops.corr_topk(corr, self.truncate_k)
-        self.corr_val, self.corr_idx = ops.corr_reorder(val, idx)
+        self._install(*ops.corr_reorder(val, idx))
         self._xyz2 = xyz2.detach().contiguous().float()
         self._xyz2p = ops.xyz_pad(self._xyz2)
 
     def set_state(self, truncated_corr, corr_idx, xyz2):
         """Install an externally built state (tests / benchmarks): corr [B,N,K] f32, idx [B,N,K] int."""
-        self.corr_val, self.corr_idx = ops.corr_reorder(truncated_corr.contiguous().float(),
-                                                        corr_idx.contiguous().to(torch.int32))
+        self._install(*ops.corr_reorder(truncated_corr.contiguous().float(), corr_idx.contiguous().to(torch.int32)))
         self._xyz2 = xyz2.contiguous().float()
         self._xyz2p = ops.xyz_pad(self._xyz2)
+
+    def _install(self, val, idx):
+        if self.state_dtype == torch.bfloat16:
+            val, idx = ops.corr_state_pack_bf16(val, idx)
+        self.corr_val, self.corr_idx = val, idx
+
+    def candidate_ids(self):
+        """[B,N,K] int64 rows of xyz2, in the stored order (the uint16 ids of the bf16 state live in an int16 tensor)."""
+        if self.corr_idx.dtype == torch.int16:
+            return self.corr_idx.to(torch.int32).bitwise_and(0xFFFF).long()
+        return self.corr_idx.long()
 
     @property
     def truncated_corr(self):
         """[B,N,K] correlation values sorted descending, as the reference keeps them (model/corr.py:38)."""
-        return None if self.corr_val is None else torch.sort(self.corr_val, dim=2, descending=True).values
+        return None if self.corr_val is None else torch.sort(self.corr_val.float(), dim=2, descending=True).values
 
     @property
     def truncate_xyz2(self):
         """[B,N,K,3] candidate coordinates, materialised on demand (model/corr.py:42)."""
         b, n, k = self.corr_idx.shape
-        idx = self.corr_idx.long().reshape(b, n * k, 1).expand(b, n * k, 3)
+        idx = self.candidate_ids().reshape(b, n * k, 1).expand(b, n * k, 3)
         return torch.gather(self._xyz2, 1, idx).reshape(b, n, k, 3)
 
     @property
     def ones_matrix(self):
-        return torch.ones_like(self.corr_val)
+        return torch.ones_like(self.corr_val, dtype=torch.float32)
 
     # ------------------------------------------------------------------------------------------
     def lookup(self, coords, **kw):

@@ -40,8 +40,8 @@ __host__ __device__ constexpr size_t lookup_warp_bytes(int K) {
 }
 
 struct LookupParams {
-    const float* corr_val;
-    const int32_t* corr_idx;
+    const void* corr_val;   // [B,N,K] f32, or bf16 bit patterns (uint16) in the reduced-precision state mode
+    const void* corr_idx;   // [B,N,K] int32, or uint16 in the reduced-precision state mode
     const float4* tab;   // [B,N] (x,y,z,0) rows of xyz2
     const float* coords; // [B,N,3]
     float* vox;          // [B,N,levels*27]
@@ -101,14 +101,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  : "memory");
 }
 
-// bring a K-float row into L2 (64 B per lane per step); it is read sparsely (valid + kNN slots) afterwards
-__device__ __forceinline__ void prefetch_row(const float* row, int K, int lane) {
-    if (K <= 512) {   // one 64-byte piece per lane covers the row
-        if (lane * 16 < K) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + lane * 16));
+// bring a row of `bytes` bytes into L2 (64 B per lane per step); it is read sparsely (valid + kNN slots) afterwards
+__device__ __forceinline__ void prefetch_row(const void* row, int bytes, int lane) {
+    const char* r = reinterpret_cast<const char*>(row);
+    if (bytes <= 2048) {   // one 64-byte piece per lane covers the row
+        if (lane * 64 < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + lane * 64));
     } else {
-        for (int o = lane * 16; o < K; o += 32 * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+        for (int o = lane * 64; o < bytes; o += 32 * 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + o));
     }
 }
+
+// element types of the per-iteration state: fp32 + int32 (8 B per candidate), or bf16 + uint16 (4 B per candidate, N <= 65536)
+template <bool HALF> struct StateT { using val = float; using idx = int32_t; };
+template <> struct StateT<true> { using val = uint16_t; using idx = uint16_t; };
+__device__ __forceinline__ float load_val(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float load_val(const uint16_t* p) { return __uint_as_float((unsigned)__ldg(p) << 16); }   // bf16 -> fp32, exact
 
 // inclusive warp scan of a word of packed 8-bit counters (no field may exceed 255)
 __device__ __forceinline__ unsigned warp_scan_packed(unsigned w, int lane) {
@@ -120,8 +127,12 @@ __device__ __forceinline__ unsigned warp_scan_packed(unsigned w, int lane) {
     return w;
 }
 
-template <int KPL, bool POW2, bool SMEM_TAB>
+template <int KPL, bool POW2, bool SMEM_TAB, bool HALF>
 __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupParams p) {
+    using val_t = typename StateT<HALF>::val;
+    using idx_t = typename StateT<HALF>::idx;
+    const val_t* g_val = reinterpret_cast<const val_t*>(p.corr_val);
+    const idx_t* g_idx = reinterpret_cast<const idx_t*>(p.corr_idx);
     constexpr int VEC = KPL >= 4 ? 4 : KPL;   // consecutive candidates per lane per block
     constexpr int NJ = KPL / VEC;             // blocks of 32*VEC candidates
     constexpr int K = KPL * 32;
@@ -210,10 +221,10 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
         if (dyn && active_warp) { pt0 = claim_chunk(); nxt0 = pt0 + 1; left0 = kChunk - 2; }
         if (active_warp && pt0 < seg_end) {   // kick off this warp's first row
             if (lane == 0) {
-                mbar_expect_tx(s_bar, K * 4);
-                bulk_g2s(s_stage, p.corr_idx + pt0 * K, K * 4, s_bar);
+                mbar_expect_tx(s_bar, K * sizeof(idx_t));
+                bulk_g2s(s_stage, g_idx + pt0 * K, K * sizeof(idx_t), s_bar);
             }
-            prefetch_row(p.corr_val + pt0 * K, K, lane);
+            prefetch_row(g_val + pt0 * K, K * sizeof(val_t), lane);
         }
         if (SMEM_TAB) { mbar_wait(&s_tabbar, tab_phase); tab_phase ^= 1u; }
         __syncthreads();   // s_next
@@ -228,8 +239,8 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                 const float cx = __ldg(p.coords + pt * 3 + 0);
                 const float cy = __ldg(p.coords + pt * 3 + 1);
                 const float cz = __ldg(p.coords + pt * 3 + 2);
-                const float* rv = p.corr_val + pt * K;
-                const int32_t* ri = p.corr_idx + pt * K;
+                const val_t* rv = g_val + pt * K;
+                const idx_t* ri = g_idx + pt * K;
                 if (p.dbg_cube) {
                     for (int i = lane; i < K * L; i += 32) p.dbg_cube[pt * K * L + i] = (int8_t)-1;
                 }
@@ -248,12 +259,15 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     int ci[VEC];
-                    if (VEC == 4) {
+                    if (VEC == 4 && HALF) {
+                        const uint2 c = reinterpret_cast<const uint2*>(s_stage)[j * 32 + lane];   // four uint16 ids
+                        ci[0] = (int)(c.x & 0xFFFFu); ci[1 % VEC] = (int)(c.x >> 16); ci[2 % VEC] = (int)(c.y & 0xFFFFu); ci[3 % VEC] = (int)(c.y >> 16);
+                    } else if (VEC == 4) {
                         const int4 c = reinterpret_cast<const int4*>(s_stage)[j * 32 + lane];
                         ci[0] = c.x; ci[1 % VEC] = c.y; ci[2 % VEC] = c.z; ci[3 % VEC] = c.w;
                     } else {
 #pragma unroll
-                        for (int s = 0; s < VEC; ++s) ci[s] = s_stage[j * 32 * VEC + lane * VEC + s];
+                        for (int s = 0; s < VEC; ++s) ci[s] = (int)reinterpret_cast<const idx_t*>(s_stage)[j * 32 * VEC + lane * VEC + s];
                     }
 #pragma unroll
                     for (int s = 0; s < VEC; ++s) {
@@ -283,10 +297,10 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                 if (nxt < seg_end) {
                     if (lane == 0) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        mbar_expect_tx(s_bar, K * 4);
-                        bulk_g2s(s_stage, p.corr_idx + nxt * K, K * 4, s_bar);
+                        mbar_expect_tx(s_bar, K * sizeof(idx_t));
+                        bulk_g2s(s_stage, g_idx + nxt * K, K * sizeof(idx_t), s_bar);
                     }
-                    prefetch_row(p.corr_val + nxt * K, K, lane);   // correlation row -> L2; read sparsely below
+                    prefetch_row(g_val + nxt * K, K * sizeof(val_t), lane);   // correlation row -> L2; read sparsely below
                 }
 
                 // ---- voxel means -----------------------------------------------------------------------
@@ -327,8 +341,8 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                         float val = 0.f;
                         if (lane < n) {
                             const int slot = s_vlist[c0 + lane];
-                            const int id = __ldg(ri + slot);
-                            val = __ldg(rv + slot);
+                            const int id = (int)__ldg(ri + slot);
+                            val = load_val(rv + slot);
                             const float4 q = SMEM_TAB ? s_tab[id] : __ldg(tab_g + id);
                             const float dx = __fsub_rn(q.x, cx), dy = __fsub_rn(q.y, cy), dz = __fsub_rn(q.z, cz);
 #pragma unroll
@@ -477,8 +491,8 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
                 __syncwarp();
                 {
                     const int slot = s_slots[lane];
-                    const float c = __ldg(rv + slot);
-                    const int id = __ldg(ri + slot);
+                    const float c = load_val(rv + slot);
+                    const int id = (int)__ldg(ri + slot);
                     const float4 q = SMEM_TAB ? s_tab[id] : __ldg(tab_g + id);
                     const float dx = __fsub_rn(q.x, cx), dy = __fsub_rn(q.y, cy), dz = __fsub_rn(q.z, cz);
                     p.knn_sel[pt * 32 + lane] = make_float4(c, dx, dy, dz);
@@ -614,7 +628,7 @@ static float cube_threshold(float r) {
     return t;
 }
 
-template <int KPL, bool POW2>
+template <int KPL, bool POW2, bool HALF>
 static int launch_lookup(LookupParams& p, cudaStream_t st) {
     const int K = KPL * 32;
     const size_t per_warp = lookup_warp_bytes(K);
@@ -636,11 +650,11 @@ static int launch_lookup(LookupParams& p, cudaStream_t st) {
     if (grid < 1) grid = 1;
     int rc;
     if (smem_tab) {
-        auto k = k_corr_lookup<KPL, POW2, true>;
+        auto k = k_corr_lookup<KPL, POW2, true, HALF>;
         if ((rc = opt_in_smem(k, smem))) return rc;
         launch_pdl(k, grid, kLookupThreads, smem, st, p);
     } else {
-        auto k = k_corr_lookup<KPL, POW2, false>;
+        auto k = k_corr_lookup<KPL, POW2, false, HALF>;
         if ((rc = opt_in_smem(k, smem))) return rc;
         launch_pdl(k, grid, kLookupThreads, smem, st, p);
     }
@@ -675,16 +689,16 @@ extern "C" int pvraft_xyz_pad_fwd(const float* xyz, int64_t rows, float* out, vo
     return check_launch("xyz_pad");
 }
 
-extern "C" int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr_idx, const float* xyz2_pad,
-                                      const float* coords, int B, int N, int K, int levels, float base_scale,
-                                      float* vox, int vox_ld, float* knn_sel, int32_t* knn_slot, double* moments,
-                                      int8_t* dbg_cube, void* stream) {
+static int corr_lookup_any(const void* corr_val, const void* corr_idx, bool half, const float* xyz2_pad, const float* coords, int B, int N,
+                           int K, int levels, float base_scale, float* vox, int vox_ld, float* knn_sel, int32_t* knn_slot, double* moments,
+                           int8_t* dbg_cube, void* stream) {
     if (!corr_val || !corr_idx || !xyz2_pad || !coords || !vox || !knn_sel) return fail(PVRAFT_ERR_BAD_ARG, "corr_lookup: null pointer");
     if (B <= 0 || N <= 0) return fail(PVRAFT_ERR_BAD_ARG, "corr_lookup: B=%d N=%d", B, N);
     if (levels < 1 || levels > 4) return fail(PVRAFT_ERR_UNSUPPORTED, "corr_lookup: levels=%d (1..4 supported)", levels);
     if (!(base_scale > 0.f)) return fail(PVRAFT_ERR_BAD_ARG, "corr_lookup: base_scale must be > 0");
     if ((reinterpret_cast<uintptr_t>(xyz2_pad) & 15u) || (reinterpret_cast<uintptr_t>(corr_idx) & 15u))
         return fail(PVRAFT_ERR_BAD_ARG, "corr_lookup: xyz2_pad and corr_idx must be 16-byte aligned (bulk copies)");
+    if (half && N > 65536) return fail(PVRAFT_ERR_UNSUPPORTED, "corr_lookup: uint16 candidate ids need N <= 65536 (N=%d)", N);
     LookupParams p{};
     p.corr_val = corr_val; p.corr_idx = corr_idx; p.tab = reinterpret_cast<const float4*>(xyz2_pad); p.coords = coords;
     p.vox = vox; p.knn_sel = reinterpret_cast<float4*>(knn_sel); p.knn_slot = knn_slot; p.moments = moments;
@@ -704,7 +718,20 @@ extern "C" int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr
     cudaStream_t st = (cudaStream_t)stream;
 #define PVRAFT_LOOKUP_CASE(KPL_)                                                            \
     case KPL_ * 32:                                                                         \
-        return pow2 ? launch_lookup<KPL_, true>(p, st) : launch_lookup<KPL_, false>(p, st);
+        return pow2 ? launch_lookup<KPL_, true, false>(p, st) : launch_lookup<KPL_, false, false>(p, st);
+#define PVRAFT_LOOKUP_CASE_H(KPL_)                                                          \
+    case KPL_ * 32:                                                                         \
+        return pow2 ? launch_lookup<KPL_, true, true>(p, st) : launch_lookup<KPL_, false, true>(p, st);
+    if (half) {
+        switch (K) {
+            PVRAFT_LOOKUP_CASE_H(4)
+            PVRAFT_LOOKUP_CASE_H(8)
+            PVRAFT_LOOKUP_CASE_H(16)
+            PVRAFT_LOOKUP_CASE_H(32)
+            default:
+                return fail(PVRAFT_ERR_UNSUPPORTED, "corr_lookup (bf16 state): truncate_k=%d (supported: 128,256,512,1024)", K);
+        }
+    }
     switch (K) {
         PVRAFT_LOOKUP_CASE(1)
         PVRAFT_LOOKUP_CASE(2)
@@ -716,4 +743,38 @@ extern "C" int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr
             return fail(PVRAFT_ERR_UNSUPPORTED, "corr_lookup: truncate_k=%d (supported: 32,64,128,256,512,1024)", K);
     }
 #undef PVRAFT_LOOKUP_CASE
+#undef PVRAFT_LOOKUP_CASE_H
+}
+
+extern "C" int pvraft_corr_lookup_fwd(const float* corr_val, const int32_t* corr_idx, const float* xyz2_pad,
+                                      const float* coords, int B, int N, int K, int levels, float base_scale,
+                                      float* vox, int vox_ld, float* knn_sel, int32_t* knn_slot, double* moments,
+                                      int8_t* dbg_cube, void* stream) {
+    return corr_lookup_any(corr_val, corr_idx, false, xyz2_pad, coords, B, N, K, levels, base_scale, vox, vox_ld, knn_sel, knn_slot, moments,
+                           dbg_cube, stream);
+}
+
+extern "C" int pvraft_corr_lookup_bf16_fwd(const uint16_t* corr_val_bf16, const uint16_t* corr_idx_u16, const float* xyz2_pad,
+                                           const float* coords, int B, int N, int K, int levels, float base_scale,
+                                           float* vox, int vox_ld, float* knn_sel, int32_t* knn_slot, double* moments,
+                                           int8_t* dbg_cube, void* stream) {
+    return corr_lookup_any(corr_val_bf16, corr_idx_u16, true, xyz2_pad, coords, B, N, K, levels, base_scale, vox, vox_ld, knn_sel, knn_slot,
+                           moments, dbg_cube, stream);
+}
+
+// fp32 correlation values -> bf16 (round to nearest even), int32 candidate ids -> uint16: the 4-byte-per-candidate state
+__global__ void k_state_pack_bf16(const float* __restrict__ val, const int32_t* __restrict__ idx, long long n, uint16_t* __restrict__ val_out,
+                                  uint16_t* __restrict__ idx_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned u = __float_as_uint(__ldg(val + i));
+    const unsigned r = u + 0x7FFFu + ((u >> 16) & 1u);            // round to nearest even on the dropped 16 bits
+    val_out[i] = (u & 0x7F800000u) == 0x7F800000u ? (uint16_t)(u >> 16) : (uint16_t)(r >> 16);   // inf / nan pass through
+    idx_out[i] = (uint16_t)__ldg(idx + i);
+}
+
+extern "C" int pvraft_corr_state_pack_bf16(const float* val, const int32_t* idx, int64_t n, uint16_t* val_out, uint16_t* idx_out, void* stream) {
+    if (!val || !idx || !val_out || !idx_out || n <= 0) return fail(PVRAFT_ERR_BAD_ARG, "corr_state_pack_bf16: bad argument");
+    k_state_pack_bf16<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(val, idx, n, val_out, idx_out);
+    return check_launch("corr_state_pack_bf16");
 }

@@ -87,6 +87,17 @@ def corr_reorder(val, idx):
     return val_out, idx_out
 
 
+def corr_state_pack_bf16(val, idx):
+    """Reordered fp32 / int32 state -> (bf16 values, uint16 ids held in an int16 tensor): 4 B per candidate and iteration."""
+    if int(idx.shape[1]) > 65536:
+        raise ValueError('uint16 candidate ids need N <= 65536')
+    v16 = torch.empty(val.shape, dtype=torch.bfloat16, device=val.device)
+    i16 = torch.empty(idx.shape, dtype=torch.int16, device=idx.device)
+    _count(lib().pvraft_corr_state_pack_bf16(_p(val), _p(idx, torch.int32), val.numel(), _p(v16, torch.bfloat16), _p(i16, torch.int16),
+                                             _stream()), 'corr_state_pack_bf16')
+    return v16, i16
+
+
 def corr_matmul(fmap1_pm, fmap2_pm):
     """Point-major feature maps [B,N,C] -> all-pairs correlation [B,N,N] / sqrt(C) on tcgen05 (3xTF32)."""
     b, n, c = fmap1_pm.shape
@@ -130,9 +141,15 @@ def corr_lookup(corr_val, corr_idx, xyz2_pad, coords, levels, base_scale, vox=No
         moments = new_stats(b, dev, 1).view(b, MOMENTS) if MOMENTS == 16 else torch.zeros(b, MOMENTS, dtype=torch.float64, device=dev)
     slots = torch.empty(b, n, KNN, dtype=torch.int32, device=dev) if want_slots else None
     cube = torch.empty(b, n, k, levels, dtype=torch.int8, device=dev) if want_cube else None
-    _count(lib().pvraft_corr_lookup_fwd(_p(corr_val), _p(corr_idx, torch.int32), _p(xyz2_pad), _p(coords), b, n, k, levels,
-                                        float(base_scale), _p(vox), vox.shape[-1], _p(knn_sel), _p(slots, torch.int32),
-                                        _p(moments, torch.float64), _p(cube, torch.int8), _stream()), 'corr_lookup')
+    if corr_val.dtype == torch.bfloat16:      # reduced-precision state: bf16 values + uint16 ids (stored as int16)
+        _count(lib().pvraft_corr_lookup_bf16_fwd(_p(corr_val, torch.bfloat16), _p(corr_idx, torch.int16), _p(xyz2_pad), _p(coords), b, n,
+                                                 k, levels, float(base_scale), _p(vox), vox.shape[-1], _p(knn_sel),
+                                                 _p(slots, torch.int32), _p(moments, torch.float64), _p(cube, torch.int8), _stream()),
+               'corr_lookup_bf16')
+    else:
+        _count(lib().pvraft_corr_lookup_fwd(_p(corr_val), _p(corr_idx, torch.int32), _p(xyz2_pad), _p(coords), b, n, k, levels,
+                                            float(base_scale), _p(vox), vox.shape[-1], _p(knn_sel), _p(slots, torch.int32),
+                                            _p(moments, torch.float64), _p(cube, torch.int8), _stream()), 'corr_lookup')
     return dict(vox=vox, knn_sel=knn_sel, moments=moments, knn_slot=slots, cube=cube)
 
 

@@ -50,6 +50,16 @@ class _RaftBase(nn.Module):
     def reset_graphs(self):
         self.__dict__.pop('_graphs', None)
 
+    def set_precision(self, mode):
+        """'fp32' (default): the reference's arithmetic.  'bf16': the reduced-precision STATE mode of BASELINE.json configs[2] --
+        the truncated correlation is kept as bf16 values + uint16 candidate ids (4 B instead of 8 B per candidate and iteration,
+        the lookup kernel's whole HBM stream); coordinates, index math and every layer stay fp32.  Inference only."""
+        if mode not in ('fp32', 'bf16'):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.corr_block.state_dtype = torch.bfloat16 if mode == 'bf16' else torch.float32
+        self.reset_graphs()
+        return self
+
     def _graphed(self, p, num_iters):
         xyz1, xyz2 = p[0].detach().contiguous().float(), p[1].detach().contiguous().float()
         graphs = self.__dict__.setdefault('_graphs', {})

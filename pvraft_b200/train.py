@@ -249,6 +249,8 @@ def rsf_forward(model, p, num_iters):
         raise ValueError('expected p = [xyz1 [B,N,3], xyz2 [B,N,3]]')
     b, n, _ = xyz1.shape
     cb = model.corr_block
+    if cb.state_dtype != torch.float32:
+        raise NotImplementedError("training differentiates through the fp32 state: call model.set_precision('fp32')")
     both = torch.cat([xyz1, xyz2], 0)
     g_both = Graph.construct_graph(both, 32)                                   # :25-26 (one batch of 2B clouds)
     fmap = flot_encoder(model.feature_extractor, both, g_both)
