@@ -321,9 +321,12 @@ PVRAFT_API int pvraft_gru_fwd(const pvraft_gru_args* a, void* stream);
  *   fc1p [B,N,C], nbr [B,N,32] int32 (LOCAL neighbour ids), edge_feats [B,N,32,3] (= graph.edge_feats),
  *   w_fc1 [C,cin+3] (columns cin..cin+2 are read)
  *   -> ymax, ymin [B,N,C]; stats [B,8,2] accumulated.   C % 8 == 0, C <= 128.
+ *   order [B,N] int32 or NULL: the LOCAL point processed r-th in every sample (pvraft_point_order_fwd: a Morton rank table).
+ *   It changes no result, only which points a CTA works on at the same time, so that their overlapping neighbourhoods are
+ *   gathered from L1 instead of L2.
  * --------------------------------------------------------------------------------------------- */
 PVRAFT_API int pvraft_setconv_edge_fwd(const float* fc1p, const int32_t* nbr, const float* edge_feats, const float* w_fc1, int cin,
-                            int B, int N, int C, float* ymax, float* ymin, double* stats, void* stream);
+                            int B, int N, int C, float* ymax, float* ymin, double* stats, const int32_t* order, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * FlowHead output stage + RAFT coordinate update.  Replaces model/update.py:69,71-72 (conv1, cat,

@@ -16,7 +16,7 @@ constexpr int kTopkThreads = 256;
 
 __device__ __forceinline__ unsigned f2key(float f) {
     const unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // larger float -> larger key
+    return u ^ ((unsigned)((int)u >> 31) | 0x80000000u);   // negatives: all bits flipped, others: sign bit set -> larger float, larger key
 }
 __device__ __forceinline__ float key2f(unsigned k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
@@ -122,7 +122,10 @@ __global__ void __launch_bounds__(kTopkThreads) k_corr_topk_vec(const float* __r
                                                                 int32_t* __restrict__ idx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* s_key = reinterpret_cast<uint4*>(smem_raw);   // [8 * 256]
-    __shared__ int s_hist[2048];
+    constexpr int kCand = 1024;                          // capacity of the candidate list of the second and third pass
+    __shared__ int s_hist[2048 + kTopkThreads];          // 2048 bins + one private sink per thread (see below)
+    __shared__ unsigned s_cand[kCand];
+    __shared__ int s_ncand;
     __shared__ int s_wsum[kTopkThreads / 32];
     __shared__ unsigned s_scan[kTopkThreads / 32][7];
     __shared__ unsigned s_prefix;
@@ -140,67 +143,99 @@ __global__ void __launch_bounds__(kTopkThreads) k_corr_topk_vec(const float* __r
         }
         s_key[c4] = kk;
     }
-    // ---- radix select (each thread only ever reads the keys it wrote) ----
-    // select(sample, floor, need): the need-th largest key among the sample keys (one per thread) or among all keys >= floor.
-    auto select = [&](bool sample, unsigned floor_key, int need, int& need_out) -> unsigned {
-        unsigned prefix = 0u;
-#pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
-            const int bits = pass < 2 ? 11 : 10;
-            const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
-            const unsigned digit_mask = (1u << bits) - 1u;
-            const unsigned hi_mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + bits));
-            for (int i = tid; i < 2048; i += kTopkThreads) s_hist[i] = 0;
-            __syncthreads();
-            if (sample) {
-                const unsigned kx = s_key[tid].x;
-                if ((kx & hi_mask) == prefix) atomicAdd(&s_hist[(kx >> shift) & digit_mask], 1);
-            } else {
+    if (tid == 0) s_ncand = 0;
+    // ---- radix select, 11 + 11 + 10 bits (each thread only ever reads the keys it wrote) ----
+    // Only the first pass looks at every key.  Its increments are UNCONDITIONAL shared-memory atomics -- keys that do not take
+    // part add to the thread's private sink bin instead of being skipped, because an `if` around a shared-memory atomic
+    // compiles to a branch + reconvergence per key.  The keys that fall into the bin of the K-th largest (a few hundred of
+    // 8192) are then collected once, and the second and third pass run over that list; a list overflow (more than 1024
+    // keys share their top 11 bits: near-constant rows) falls back to scanning the row again.
+    const int sink = 2048 + tid;
+    // locate, with block-wide suffix sums over the 2048 bins, the bin holding the need-th largest counted key
+    auto find_bin = [&](unsigned prefix, int shift, int need) {
+        int h[8], mine = 0;   // thread t owns bins 8t .. 8t+7
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint4 kk = s_key[j * kTopkThreads + tid];
-                    if (kk.x >= floor_key && (kk.x & hi_mask) == prefix) atomicAdd(&s_hist[(kk.x >> shift) & digit_mask], 1);
-                    if (kk.y >= floor_key && (kk.y & hi_mask) == prefix) atomicAdd(&s_hist[(kk.y >> shift) & digit_mask], 1);
-                    if (kk.z >= floor_key && (kk.z & hi_mask) == prefix) atomicAdd(&s_hist[(kk.z >> shift) & digit_mask], 1);
-                    if (kk.w >= floor_key && (kk.w & hi_mask) == prefix) atomicAdd(&s_hist[(kk.w >> shift) & digit_mask], 1);
-                }
-            }
-            __syncthreads();
-            // thread t owns bins 8t .. 8t+7; block-wide suffix sums locate the bin holding the `need`-th largest key
-            int h[8], mine = 0;
+        for (int q = 0; q < 8; ++q) { h[q] = s_hist[tid * 8 + q]; mine += h[q]; }
+        int incl = mine;   // inclusive suffix sum over the lanes >= lane of this warp
 #pragma unroll
-            for (int q = 0; q < 8; ++q) { h[q] = s_hist[tid * 8 + q]; mine += h[q]; }
-            int incl = mine;   // inclusive suffix sum over the lanes >= lane of this warp
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int a = __shfl_down_sync(kFull, incl, o);
-                if (lane + o < 32) incl += a;
-            }
-            if (lane == 0) s_wsum[w] = incl;
-            __syncthreads();
-            int above = incl;
-            for (int ww = w + 1; ww < kTopkThreads / 32; ++ww) above += s_wsum[ww];
-            const int higher = above - mine;   // keys in bins owned by higher threads
-            if (higher < need && above >= need) {
-                int acc = higher, bin = 7;
-                for (; bin > 0; --bin) {
-                    if (acc + h[bin] >= need) break;
-                    acc += h[bin];
-                }
-                s_need = need - acc;   // rank of the target inside the chosen bin
-                s_prefix = prefix | ((unsigned)(tid * 8 + bin) << shift);
-            }
-            __syncthreads();
-            prefix = s_prefix;
-            need = s_need;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_down_sync(kFull, incl, o);
+            if (lane + o < 32) incl += a;
         }
-        need_out = need;
-        return prefix;
+        if (lane == 0) s_wsum[w] = incl;
+        __syncthreads();
+        int above = incl;
+        for (int ww = w + 1; ww < kTopkThreads / 32; ++ww) above += s_wsum[ww];
+        const int higher = above - mine;   // keys in bins owned by higher threads
+        if (higher < need && above >= need) {
+            int acc = higher, bin = 7;
+            for (; bin > 0; --bin) {
+                if (acc + h[bin] >= need) break;
+                acc += h[bin];
+            }
+            s_need = need - acc;   // rank of the target inside the chosen bin
+            s_prefix = prefix | ((unsigned)(tid * 8 + bin) << shift);
+        }
+        __syncthreads();
     };
+    for (int i = tid; i < 2048; i += kTopkThreads) s_hist[i] = 0;
     __syncthreads();
-    const unsigned floor_key = 0u;   // (a sampled floor that skips most atomics was tried: the extra passes cost more than they save)
-    int need = 0;
-    const unsigned prefix = select(false, floor_key, K, need);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint4 kk = s_key[j * kTopkThreads + tid];
+        atomicAdd(&s_hist[kk.x >> 21], 1);
+        atomicAdd(&s_hist[kk.y >> 21], 1);
+        atomicAdd(&s_hist[kk.z >> 21], 1);
+        atomicAdd(&s_hist[kk.w >> 21], 1);
+    }
+    __syncthreads();
+    find_bin(0u, 21, K);
+    unsigned prefix = s_prefix;
+    int need = s_need;
+    {   // candidates of the remaining passes: keys whose top 11 bits equal the chosen bin
+        const unsigned top = prefix >> 21;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint4 kk = s_key[j * kTopkThreads + tid];
+            const unsigned ke[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if ((ke[e] >> 21) == top) {
+                    const int at = atomicAdd(&s_ncand, 1);
+                    if (at < kCand) s_cand[at] = ke[e];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int ncand = s_ncand;
+#pragma unroll 1
+    for (int pass = 1; pass < 3; ++pass) {
+        const int shift = pass == 1 ? 10 : 0;
+        const unsigned digit_mask = pass == 1 ? 0x7FFu : 0x3FFu;
+        const unsigned hi_mask = 0xFFFFFFFFu << (shift + (pass == 1 ? 11 : 10));
+        for (int i = tid; i < 2048; i += kTopkThreads) s_hist[i] = 0;
+        __syncthreads();
+        if (ncand <= kCand) {
+            for (int i = tid; i < ncand; i += kTopkThreads) {
+                const unsigned k = s_cand[i];
+                atomicAdd(&s_hist[(k & hi_mask) == prefix ? (int)((k >> shift) & digit_mask) : sink], 1);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint4 kk = s_key[j * kTopkThreads + tid];
+                atomicAdd(&s_hist[(kk.x & hi_mask) == prefix ? (int)((kk.x >> shift) & digit_mask) : sink], 1);
+                atomicAdd(&s_hist[(kk.y & hi_mask) == prefix ? (int)((kk.y >> shift) & digit_mask) : sink], 1);
+                atomicAdd(&s_hist[(kk.z & hi_mask) == prefix ? (int)((kk.z >> shift) & digit_mask) : sink], 1);
+                atomicAdd(&s_hist[(kk.w & hi_mask) == prefix ? (int)((kk.w >> shift) & digit_mask) : sink], 1);
+            }
+        }
+        __syncthreads();
+        find_bin(prefix, shift, need);
+        prefix = s_prefix;
+        need = s_need;
+    }
     const unsigned T = prefix;   // exact K-th largest key
     const int need_eq = need;    // how many keys == T belong to the top-K (lowest columns first)
     // ---- ordered compaction: chunk j = columns [1024 j, 1024 j + 1024), inside a chunk thread order = column order ----

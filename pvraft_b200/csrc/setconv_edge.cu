@@ -53,7 +53,8 @@ template <int PAIRS>
 __global__ void __launch_bounds__(kEdgeThreads, PAIRS == 1 ? 6 : 4) k_setconv_edge_pairs(const float* __restrict__ fc1p, const int32_t* __restrict__ nbr,
                                                                      const float* __restrict__ edge_feats, const float* __restrict__ w_fc1,
                                                                      int cin, int B, int N, int C, float* __restrict__ ymax,
-                                                                     float* __restrict__ ymin, double* __restrict__ stats) {
+                                                                     float* __restrict__ ymin, double* __restrict__ stats,
+                                                                     const int32_t* __restrict__ order, int sm_n) {
     __shared__ double s_part[kEdgeThreads / 32][128][2];
     __shared__ __align__(16) float4 s_edge[kEdgeThreads / 32][32];   // (neighbour id bits, ex, ey, ez) of the warp's point
     pdl_trigger();   // the next kernel may be staged while this one drains
@@ -73,7 +74,15 @@ __global__ void __launch_bounds__(kEdgeThreads, PAIRS == 1 ? 6 : 4) k_setconv_ed
     for (int q = 0; q < PAIRS; ++q) { wx2[q] = pk(wx[q].x, wx[q].y); wy2[q] = pk(wy[q].x, wy[q].y); wz2[q] = pk(wz[q].x, wz[q].y); }
     const long long total = (long long)B * N;
     long long pt_begin, pt_end;
-    split_range(total, gridDim.x, blockIdx.x, pt_begin, pt_end);
+    {
+        // CTAs are dealt to the SMs round-robin, so blockIdx b, b + #SM, b + 2 #SM ... share an SM (and its L1): give those
+        // CTAs ADJACENT ranges of the processing order, so that co-resident CTAs gather overlapping neighbourhoods too
+        const int sms = sm_n > 0 ? sm_n : (int)gridDim.x;
+        const int per = ((int)gridDim.x + sms - 1) / sms;
+        int slot = ((int)blockIdx.x % sms) * per + (int)blockIdx.x / sms;
+        if ((int)gridDim.x % sms != 0) slot = (int)blockIdx.x;   // ragged grid: plain contiguous ranges
+        split_range(total, gridDim.x, slot, pt_begin, pt_end);
+    }
     long long seg = pt_begin;
     while (seg < pt_end) {
         const int b = (int)(seg / N);
@@ -87,8 +96,11 @@ __global__ void __launch_bounds__(kEdgeThreads, PAIRS == 1 ? 6 : 4) k_setconv_ed
 #pragma unroll
         for (int q = 0; q < PAIRS; ++q) { on[q] = 2 * lane + 64 * q < C; coff[q] = on[q] ? 2 * lane + 64 * q : 0; }
         const float* P = fc1p + (size_t)b * N * C;
-        for (long long pt = seg + w; pt < seg_end; pt += nwarps) {
-            const int i = (int)(pt - (long long)b * N);
+        for (long long r = seg + w; r < seg_end; r += nwarps) {
+            // processing order: with `order` (a space-filling-curve rank -> point table) the 8 warps of a CTA work on spatial
+            // neighbours at the same time, whose 32-neighbourhoods overlap: their gathers hit the same rows in L1
+            const int i = order ? __ldg(order + r) : (int)(r - (long long)b * N);
+            const long long pt = (long long)b * N + i;
             // lane e parks neighbour e: id and edge feature x_j - x_i (graph.edge_feats, gconv.py:66)
             const float* ef = edge_feats + ((size_t)pt * 32 + lane) * 3;
             __syncwarp();
@@ -162,7 +174,7 @@ __global__ void __launch_bounds__(kEdgeThreads, PAIRS == 1 ? 6 : 4) k_setconv_ed
 using namespace pvraft;
 
 extern "C" int pvraft_setconv_edge_fwd(const float* fc1p, const int32_t* nbr, const float* edge_feats, const float* w_fc1, int cin,
-                                       int B, int N, int C, float* ymax, float* ymin, double* stats, void* stream) {
+                                       int B, int N, int C, float* ymax, float* ymin, double* stats, const int32_t* order, void* stream) {
     if (!fc1p || !nbr || !edge_feats || !w_fc1 || !ymax || !ymin || !stats) return fail(PVRAFT_ERR_BAD_ARG, "setconv_edge: null pointer");
     if (B <= 0 || N <= 0 || cin <= 0) return fail(PVRAFT_ERR_BAD_ARG, "setconv_edge: bad shape");
     if (C <= 0 || C > 128 || C % PVRAFT_GN_GROUPS) return fail(PVRAFT_ERR_UNSUPPORTED, "setconv_edge: C=%d (multiple of 8, <= 128)", C);
@@ -173,11 +185,11 @@ extern "C" int pvraft_setconv_edge_fwd(const float* fc1p, const int32_t* nbr, co
     const int grid = (int)(g < 1 ? 1 : g);
     cudaStream_t st = (cudaStream_t)stream;
     if (C <= 64) {
-        launch_pdl(k_setconv_edge_pairs<1>, grid, kEdgeThreads, 0, st, fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats);
+        launch_pdl(k_setconv_edge_pairs<1>, grid, kEdgeThreads, 0, st, fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats, order, order ? sm_count() : 0);
         return check_launch("setconv_edge");
     }
     if (C <= 128) {
-        launch_pdl(k_setconv_edge_pairs<2>, grid, kEdgeThreads, 0, st, fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats);
+        launch_pdl(k_setconv_edge_pairs<2>, grid, kEdgeThreads, 0, st, fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats, order, order ? sm_count() : 0);
         return check_launch("setconv_edge");
     }
     return fail(PVRAFT_ERR_UNSUPPORTED, "setconv_edge: C=%d", C);

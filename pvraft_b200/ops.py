@@ -229,17 +229,18 @@ def derived(tensors, tag, fn):
     return value
 
 
-def point_order(points):
-    """[B,N,3] -> [B,N] int64: Morton order over the cells of the kNN grid, from the library's in-shared-memory sort (one
-    launch; the torch formulation below costs ~40 launches)."""
+def point_order(points, as_int32=False):
+    """[B,N,3] -> [B,N] int64 (int32 with as_int32): Morton order over the cells of the kNN grid, from the library's
+    in-shared-memory sort (one launch; the torch formulation below costs ~40 launches)."""
     b, n, _ = points.shape
     ws_bytes = int(lib().pvraft_knn_workspace_bytes(b, n))
     if ws_bytes <= 0 or n < 64:
-        return morton_order(points)
+        perm = morton_order(points)
+        return perm.to(torch.int32).contiguous() if as_int32 else perm
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=points.device)
     perm = torch.empty(b, n, dtype=torch.int32, device=points.device)
     _count(lib().pvraft_point_order_fwd(_p(points), b, n, _p(perm, torch.int32), _p(ws, torch.uint8), _stream()), 'point_order')
-    return perm.long()
+    return perm if as_int32 else perm.long()
 
 
 def morton_order(points):
@@ -325,14 +326,14 @@ def flow_out(args):
     _count(lib().pvraft_flow_out_fwd(C.byref(args), _stream()), 'flow_out')
 
 
-def setconv_edge(fc1p, nbr, edge_feats, w_fc1, cin, stats, ymax=None, ymin=None):
+def setconv_edge(fc1p, nbr, edge_feats, w_fc1, cin, stats, ymax=None, ymin=None, order=None):
     b, n, c = fc1p.shape
     if ymax is None:
         ymax = torch.empty_like(fc1p)
     if ymin is None:
         ymin = torch.empty_like(fc1p)
     _count(lib().pvraft_setconv_edge_fwd(_p(fc1p), _p(nbr, torch.int32), _p(edge_feats), _p(w_fc1), cin, b, n, c, _p(ymax),
-                                         _p(ymin), _p(stats, torch.float64), _stream()), 'setconv_edge')
+                                         _p(ymin), _p(stats, torch.float64), _p(order, torch.int32), _stream()), 'setconv_edge')
     return ymax, ymin
 
 

@@ -124,7 +124,8 @@ class _RaftBase(nn.Module):
         both = torch.cat([xyz1, xyz2], 0)
         fmap, graph2 = self.feature_extractor(both, point_major=True)
         fmap1, fmap2 = fmap[:b], fmap[b:]
-        graph = Graph(graph2.nbr[:b], graph2._rel[:b], graph2.k_neighbors, [b * xyz1.shape[1]] * 2)   # pc1's graph
+        graph = Graph(graph2.nbr[:b], graph2._rel[:b], graph2.k_neighbors, [b * xyz1.shape[1]] * 2,
+                      None if graph2.order is None else graph2.order[:b])   # pc1's graph
         self.corr_block.init_module_pm(fmap1, fmap2, xyz2)               # :29
         # the reference rebuilds the same pc1 graph for the context encoder (:31); reuse it
         fct1, graph_context = self.context_extractor(xyz1, graph=graph, point_major=True)

@@ -254,7 +254,7 @@ def rsf_forward(model, p, num_iters):
     both = torch.cat([xyz1, xyz2], 0)
     g_both = Graph.construct_graph(both, 32)                                   # :25-26 (one batch of 2B clouds)
     fmap = flot_encoder(model.feature_extractor, both, g_both)
-    graph1 = Graph(g_both.nbr[:b].contiguous(), g_both._rel[:b].contiguous(), 32, [b * n] * 2)
+    graph1 = Graph(g_both.nbr[:b].contiguous(), g_both._rel[:b].contiguous(), 32, [b * n] * 2)   # (the training path does not use .order)
     corr_val, corr_idx = CorrInitFn.apply(fmap[:b], fmap[b:], cb.truncate_k, cb)   # :29
     xyz2p = ops.xyz_pad(xyz2)
     fct1 = flot_encoder(model.context_extractor, xyz1, graph1)                 # :31 (same cloud, same graph)
