@@ -188,26 +188,10 @@ __global__ void __launch_bounds__(kLookupThreads, 1) k_corr_lookup(const LookupP
     const int kChunk = p.chunk;
     const unsigned one = (unsigned)min(p.chunk, 1);   // == 1, but not to the compiler (see the histogram below)
 
-    // Dynamic mode: a CTA starts on "its" sample and, when that sample's points are all claimed, moves on to the following
-    // samples (one more 128 KB table load each) as long as they still have unclaimed points -- 148 CTAs over 8 samples is
-    // 18.5 per sample, and samples differ in cost, so without stealing the kernel waits ~10 % for its slowest sample.
-    __shared__ int s_peek;
-    const int b_home = dyn ? (int)(pt_begin / p.N) : 0;
-    int hop = 0;
+    // (Letting a CTA that has finished its sample adopt points of other samples -- one more 128 KB table load each -- was
+    //  measured: 104 us instead of 102.8, the kernel's tail is not a per-sample imbalance.)
     long long seg = pt_begin;
-    while (dyn ? hop < p.B : seg < pt_end) {
-        if (dyn) {
-            const int bb = (b_home + hop) % p.B;
-            ++hop;
-            seg = (long long)bb * p.N;
-            pt_end = seg + p.N;
-            if (hop > 1) {   // a foreign sample: worth a table load only if it still has work
-                __syncthreads();
-                if (threadIdx.x == 0) s_peek = *reinterpret_cast<volatile int*>(p.moments + (size_t)bb * PVRAFT_MOMENTS + 15);
-                __syncthreads();
-                if (s_peek >= p.N) continue;
-            }
-        }
+    while (seg < pt_end) {
         const int b = (int)(seg / p.N);
         long long seg_end = (long long)(b + 1) * p.N;
         if (seg_end > pt_end) seg_end = pt_end;

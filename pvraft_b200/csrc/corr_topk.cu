@@ -193,16 +193,39 @@ __global__ void __launch_bounds__(kTopkThreads) k_corr_topk_vec(const float* __r
     unsigned prefix = s_prefix;
     int need = s_need;
     {   // candidates of the remaining passes: keys whose top 11 bits equal the chosen bin
+        // (count, block scan, predicated stores: a per-key `if { atomicAdd; store }` costs a divergent branch per key)
         const unsigned top = prefix >> 21;
+        int mine = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const uint4 kk = s_key[j * kTopkThreads + tid];
-            const unsigned ke[4] = {kk.x, kk.y, kk.z, kk.w};
+            mine += ((kk.x >> 21) == top) + ((kk.y >> 21) == top) + ((kk.z >> 21) == top) + ((kk.w >> 21) == top);
+        }
+        int incl = mine;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                if ((ke[e] >> 21) == top) {
-                    const int at = atomicAdd(&s_ncand, 1);
-                    if (at < kCand) s_cand[at] = ke[e];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += a;
+        }
+        if (lane == 31) s_wsum[w] = incl;
+        __syncthreads();
+        int at = incl - mine, total = 0;
+        for (int ww = 0; ww < kTopkThreads / 32; ++ww) {
+            const int a = s_wsum[ww];
+            total += a;
+            if (ww < w) at += a;
+        }
+        if (tid == 0) s_ncand = total;
+        if (total <= kCand && mine > 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint4 kk = s_key[j * kTopkThreads + tid];
+                const unsigned ke[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool hit = (ke[e] >> 21) == top;
+                    if (hit) s_cand[at] = ke[e];
+                    at += hit ? 1 : 0;
                 }
             }
         }
@@ -279,8 +302,12 @@ __global__ void __launch_bounds__(kTopkThreads) k_corr_topk_vec(const float* __r
     }
     // Only ~K/M of the keys are kept: a float4 group without any key >= T (3 in 4 groups at K/M = 1/16) is skipped on its
     // packed counts alone, and the surviving groups store through a per-row base pointer.
-    float* vrow = val + row * (size_t)K;
-    int32_t* irow = idx + row * (size_t)K;
+    // The kept keys go to their output position in a shared-memory staging row first (the candidate list and the histogram
+    // are dead by now) and leave with coalesced stores; the scattered 4-byte global stores this replaces cost ~25
+    // instructions per kept key.
+    __syncthreads();
+    unsigned* s_oval = s_cand;                                  // [K <= 1024] keys
+    int* s_oidx = s_hist;                                       // [K <= 1024] columns
     int base_gt = 0, base_eq = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -300,12 +327,19 @@ __global__ void __launch_bounds__(kTopkThreads) k_corr_topk_vec(const float* __r
             const bool gt = key > T, eq = key == T;
             if (gt || (eq && eq_before < need_eq)) {
                 const int pos = gt_before + min(eq_before, need_eq);
-                vrow[pos] = key2f(key);
-                irow[pos] = col + e;
+                s_oval[pos] = key;
+                s_oidx[pos] = col + e;
             }
             gt_before += gt ? 1 : 0;
             eq_before += eq ? 1 : 0;
         }
+    }
+    __syncthreads();
+    float* vrow = val + row * (size_t)K;
+    int32_t* irow = idx + row * (size_t)K;
+    for (int i = tid; i < K; i += kTopkThreads) {
+        vrow[i] = key2f(s_oval[i]);
+        irow[i] = s_oidx[i];
     }
 }
 

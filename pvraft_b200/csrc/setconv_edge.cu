@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(kEdgeThreads, PAIRS == 1 ? 6 : 4) k_setconv_ed
                                                                      const float* __restrict__ edge_feats, const float* __restrict__ w_fc1,
                                                                      int cin, int B, int N, int C, float* __restrict__ ymax,
                                                                      float* __restrict__ ymin, double* __restrict__ stats,
-                                                                     const int32_t* __restrict__ order, int sm_n) {
+                                                                     const int32_t* __restrict__ order) {
     __shared__ double s_part[kEdgeThreads / 32][128][2];
     __shared__ __align__(16) float4 s_edge[kEdgeThreads / 32][32];   // (neighbour id bits, ex, ey, ez) of the warp's point
     pdl_trigger();   // the next kernel may be staged while this one drains
@@ -74,15 +74,7 @@ __global__ void __launch_bounds__(kEdgeThreads, PAIRS == 1 ? 6 : 4) k_setconv_ed
     for (int q = 0; q < PAIRS; ++q) { wx2[q] = pk(wx[q].x, wx[q].y); wy2[q] = pk(wy[q].x, wy[q].y); wz2[q] = pk(wz[q].x, wz[q].y); }
     const long long total = (long long)B * N;
     long long pt_begin, pt_end;
-    {
-        // CTAs are dealt to the SMs round-robin, so blockIdx b, b + #SM, b + 2 #SM ... share an SM (and its L1): give those
-        // CTAs ADJACENT ranges of the processing order, so that co-resident CTAs gather overlapping neighbourhoods too
-        const int sms = sm_n > 0 ? sm_n : (int)gridDim.x;
-        const int per = ((int)gridDim.x + sms - 1) / sms;
-        int slot = ((int)blockIdx.x % sms) * per + (int)blockIdx.x / sms;
-        if ((int)gridDim.x % sms != 0) slot = (int)blockIdx.x;   // ragged grid: plain contiguous ranges
-        split_range(total, gridDim.x, slot, pt_begin, pt_end);
-    }
+    split_range(total, gridDim.x, blockIdx.x, pt_begin, pt_end);   // (handing SM-mates adjacent ranges was measured: no gain)
     long long seg = pt_begin;
     while (seg < pt_end) {
         const int b = (int)(seg / N);
@@ -185,11 +177,11 @@ extern "C" int pvraft_setconv_edge_fwd(const float* fc1p, const int32_t* nbr, co
     const int grid = (int)(g < 1 ? 1 : g);
     cudaStream_t st = (cudaStream_t)stream;
     if (C <= 64) {
-        launch_pdl(k_setconv_edge_pairs<1>, grid, kEdgeThreads, 0, st, fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats, order, order ? sm_count() : 0);
+        launch_pdl(k_setconv_edge_pairs<1>, grid, kEdgeThreads, 0, st, fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats, order);
         return check_launch("setconv_edge");
     }
     if (C <= 128) {
-        launch_pdl(k_setconv_edge_pairs<2>, grid, kEdgeThreads, 0, st, fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats, order, order ? sm_count() : 0);
+        launch_pdl(k_setconv_edge_pairs<2>, grid, kEdgeThreads, 0, st, fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats, order);
         return check_launch("setconv_edge");
     }
     return fail(PVRAFT_ERR_UNSUPPORTED, "setconv_edge: C=%d", C);
