@@ -1,6 +1,7 @@
 """Turn the scratch ncu outputs under gpurun_out/ into the tracked summaries under profiles/.
 python tools/make_profiles.py <round-tag> <launch-list.csv> <lookup.ncu-rep> [<other.ncu-rep> ...]"""
 import csv
+import hashlib
 import json
 import os
 import shutil
@@ -15,7 +16,7 @@ shutil.copy(launches, os.path.join(out, f'{tag}_launches.csv'))
 txt = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'launch_summary.py'), launches, '30'],
                      capture_output=True, text=True).stdout
 open(os.path.join(out, f'{tag}_launches_summary.txt'), 'w').write(
-    'ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off python tools/profile_forward.py\n'
+    'ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv python tools/profile_forward.py\n'
     '(one RSF.forward of the bench workload: B=8, N=8192, K=512, iters=32; per-launch times are cold-cache and\n'
     'serialised: compare SHARES)\n\n' + txt)
 KEYS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
@@ -47,7 +48,9 @@ for rep in reps:
             rd = float(r[h.index('dram__bytes_read.sum')]); wr = float(r[h.index('dram__bytes_write.sum')])
             unit = rows[1][h.index('dram__bytes_read.sum')]
             mul = {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1}.get(unit, 1)
+            sha = hashlib.sha256(open(os.path.join(ROOT, 'pvraft_b200', 'csrc', 'corr_lookup.cu'), 'rb').read()).hexdigest()
             json.dump({'kernel': 'k_corr_lookup', 'source': os.path.basename(rep), 'workload': 'B=8, N=8192, K=512 (one launch)',
+                       'source_sha256': sha,
                        'dram_bytes_read': rd * mul, 'dram_bytes_write': wr * mul, 'dram_bytes_per_launch': (rd + wr) * mul},
                       open(os.path.join(out, 'lookup_dram_bytes.json'), 'w'), indent=1)
     open(os.path.join(out, f'{tag}_{name}_ncu_summary.txt'), 'w').write('\n'.join(lines))
@@ -55,9 +58,9 @@ for rep in reps:
     tmp = os.path.join(out, f'.{name}_source.csv')
     open(tmp, 'w').write(src)
     if 'lookup' in name:
-        s = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'ncu_source_summary.py'), tmp, '65536', '12'],
+        s = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'ncu_lines.py'), rep, '65536', '9'],
                            capture_output=True, text=True).stdout
         open(os.path.join(out, f'{tag}_{name}_source_hotspots.txt'), 'w').write(
-            'runs of SASS with similar execution counts (exec/pt = warp-instructions per point, B*N = 65536 points)\n' + s)
+            'per source line: warp-instructions per point (exec/pt, B*N = 65536 points), share of stall samples, shared-memory wavefronts\n' + s)
     os.remove(tmp)
 print(os.listdir(out))
