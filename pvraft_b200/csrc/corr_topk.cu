@@ -125,7 +125,6 @@ __global__ void __launch_bounds__(kTopkThreads) k_corr_topk_vec(const float* __r
     constexpr int kCand = 1024;                          // capacity of the candidate list of the second and third pass
     __shared__ int s_hist[2048 + kTopkThreads];          // 2048 bins + one private sink per thread (see below)
     __shared__ unsigned s_cand[kCand];
-    __shared__ int s_ncand;
     __shared__ int s_wsum[kTopkThreads / 32];
     __shared__ unsigned s_scan[kTopkThreads / 32][7];
     __shared__ unsigned s_prefix;
@@ -143,7 +142,6 @@ __global__ void __launch_bounds__(kTopkThreads) k_corr_topk_vec(const float* __r
         }
         s_key[c4] = kk;
     }
-    if (tid == 0) s_ncand = 0;
     // ---- radix select, 11 + 11 + 10 bits (each thread only ever reads the keys it wrote) ----
     // Only the first pass looks at every key.  Its increments are UNCONDITIONAL shared-memory atomics -- keys that do not take
     // part add to the thread's private sink bin instead of being skipped, because an `if` around a shared-memory atomic
@@ -192,6 +190,7 @@ __global__ void __launch_bounds__(kTopkThreads) k_corr_topk_vec(const float* __r
     find_bin(0u, 21, K);
     unsigned prefix = s_prefix;
     int need = s_need;
+    int ncand = 0;
     {   // candidates of the remaining passes: keys whose top 11 bits equal the chosen bin
         // (count, block scan, predicated stores: a per-key `if { atomicAdd; store }` costs a divergent branch per key)
         const unsigned top = prefix >> 21;
@@ -215,7 +214,7 @@ __global__ void __launch_bounds__(kTopkThreads) k_corr_topk_vec(const float* __r
             total += a;
             if (ww < w) at += a;
         }
-        if (tid == 0) s_ncand = total;
+        ncand = total;   // (the same value in every thread)
         if (total <= kCand && mine > 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -231,7 +230,6 @@ __global__ void __launch_bounds__(kTopkThreads) k_corr_topk_vec(const float* __r
         }
     }
     __syncthreads();
-    const int ncand = s_ncand;
 #pragma unroll 1
     for (int pass = 1; pass < 3; ++pass) {
         const int shift = pass == 1 ? 10 : 0;
