@@ -161,195 +161,6 @@ __global__ void __launch_bounds__(kEdgeThreads, PAIRS == 1 ? 6 : 4) k_setconv_ed
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Tiled variant for a spatially coherent processing order (`order` = Morton rank table, N % 32 == 0, N <= 16384).
-// A CTA works on tiles of 32 consecutive points of the order.  Their 1024 neighbour references hit only a few hundred
-// distinct rows (neighbourhoods of neighbours overlap), so the tile first builds the SET of referenced rows -- a bitmap over the
-// sample's points, a block scan of its popcounts gives every row a slot -- copies those rows from L2 into shared memory once
-// (coalesced 256-byte rows) and then gathers from shared memory: the edge loop's one global 8-byte gather per neighbour and
-// channel pair becomes a conflict-free LDS.64, and the kernel leaves the L2 -> SM gather bandwidth it was bound by.
-// A tile whose set does not fit (the curve jumped: two distant blobs) gathers from global memory like the kernel above.
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int kTileP = 32;                 // points per tile
-constexpr int kTabBytes = 80 * 1024;       // shared-memory row table
-
-template <int PAIRS>
-__global__ void __launch_bounds__(kEdgeThreads, 2) k_setconv_edge_tiled(const float* __restrict__ fc1p, const int32_t* __restrict__ nbr,
-                                                                        const float* __restrict__ edge_feats, const float* __restrict__ w_fc1,
-                                                                        int cin, int B, int N, int C, float* __restrict__ ymax,
-                                                                        float* __restrict__ ymin, double* __restrict__ stats,
-                                                                        const int32_t* __restrict__ order) {
-    extern __shared__ __align__(16) unsigned char smem_e[];
-    const int words = N >> 5;                                                     // bitmap words (<= 512)
-    float* s_tab = reinterpret_cast<float*>(smem_e);                              // [cap][C]
-    unsigned* s_bits = reinterpret_cast<unsigned*>(smem_e + kTabBytes);           // [512]
-    int* s_pref = reinterpret_cast<int*>(s_bits + 512);                           // [512] rows before word i
-    int* s_uid = s_pref + 512;                                                    // [cap <= 1280]
-    float4* s_edge = reinterpret_cast<float4*>(s_uid + 1280);                     // [8 warps][32]
-    double* s_part = reinterpret_cast<double*>(s_edge + 8 * 32);                  // [8 warps][128][2]
-    __shared__ int s_wsum[kEdgeThreads / 32];
-    __shared__ int s_total;
-    pdl_trigger();
-    pdl_wait();
-    const int lane = lane_id(), w = warp_id(), nwarps = kEdgeThreads / 32, tid = threadIdx.x;
-    const int ld = cin + 3;
-    const int cap = min(1280, kTabBytes / (C * 4));
-    unsigned long long wx2[PAIRS], wy2[PAIRS], wz2[PAIRS];
-    bool on[PAIRS];
-    int coff[PAIRS];
-#pragma unroll
-    for (int q = 0; q < PAIRS; ++q) {
-        const int c = min(2 * lane + 64 * q, C - 2);
-        wx2[q] = pk(__ldg(w_fc1 + (size_t)c * ld + cin + 0), __ldg(w_fc1 + (size_t)(c + 1) * ld + cin + 0));
-        wy2[q] = pk(__ldg(w_fc1 + (size_t)c * ld + cin + 1), __ldg(w_fc1 + (size_t)(c + 1) * ld + cin + 1));
-        wz2[q] = pk(__ldg(w_fc1 + (size_t)c * ld + cin + 2), __ldg(w_fc1 + (size_t)(c + 1) * ld + cin + 2));
-        on[q] = 2 * lane + 64 * q < C;
-        coff[q] = on[q] ? 2 * lane + 64 * q : 0;
-    }
-    const int tiles_per_sample = N / kTileP;
-    const long long n_tiles = (long long)B * tiles_per_sample;
-    long long t_begin, t_end;
-    split_range(n_tiles, gridDim.x, blockIdx.x, t_begin, t_end);
-    double dS[PAIRS][2], dSS[PAIRS][2];
-#pragma unroll
-    for (int q = 0; q < PAIRS; ++q) { dS[q][0] = dS[q][1] = 0.0; dSS[q][0] = dSS[q][1] = 0.0; }
-    int cur_b = -1;
-    auto flush = [&](int b) {   // per-channel partials of sample b -> per-group sums -> one atomic per (group, moment)
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < PAIRS; ++q) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (on[q]) {
-                    s_part[((size_t)w * 128 + 2 * lane + 64 * q + h) * 2 + 0] = dS[q][h];
-                    s_part[((size_t)w * 128 + 2 * lane + 64 * q + h) * 2 + 1] = dSS[q][h];
-                }
-                dS[q][h] = 0.0; dSS[q][h] = 0.0;
-            }
-        }
-        __syncthreads();
-        if (tid < 16) {
-            const int g = tid >> 1, m = tid & 1, gsz = C / PVRAFT_GN_GROUPS;
-            double acc = 0.0;
-            for (int c = g * gsz; c < (g + 1) * gsz; ++c)
-                for (int ww = 0; ww < nwarps; ++ww) acc += s_part[((size_t)ww * 128 + c) * 2 + m];
-            if (acc != 0.0) atomicAdd(stats + (size_t)b * 16 + tid, acc);
-        }
-    };
-    for (long long t = t_begin; t < t_end; ++t) {
-        const int b = (int)(t / tiles_per_sample);
-        if (b != cur_b) {
-            if (cur_b >= 0) flush(cur_b);
-            cur_b = b;
-        }
-        const float* P = fc1p + (size_t)b * N * C;
-        const long long r0 = t * kTileP;                       // first rank of the tile (global: b*N + rank)
-        // ---- the set of rows the tile references ----
-        __syncthreads();                                       // previous tile's readers of the table / bitmap are done
-        for (int i = tid; i < words; i += kEdgeThreads) s_bits[i] = 0u;
-        __syncthreads();
-        {
-            const int pi = tid >> 3, e4 = (tid & 7) * 4;       // point of the tile, first of this thread's 4 edges
-            const long long pt = (long long)b * N + __ldg(order + r0 + pi);
-            const int4 id = __ldg(reinterpret_cast<const int4*>(nbr + pt * 32 + e4));
-            atomicOr(&s_bits[id.x >> 5], 1u << (id.x & 31));
-            atomicOr(&s_bits[id.y >> 5], 1u << (id.y & 31));
-            atomicOr(&s_bits[id.z >> 5], 1u << (id.z & 31));
-            atomicOr(&s_bits[id.w >> 5], 1u << (id.w & 31));
-        }
-        __syncthreads();
-        {   // exclusive scan of the per-word popcounts: thread i owns words 2i, 2i+1
-            const unsigned b0 = 2 * tid < words ? s_bits[2 * tid] : 0u, b1 = 2 * tid + 1 < words ? s_bits[2 * tid + 1] : 0u;
-            const int c0 = __popc(b0), c1 = __popc(b1);
-            int incl = c0 + c1;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int a = __shfl_up_sync(kFull, incl, o);
-                if (lane >= o) incl += a;
-            }
-            if (lane == 31) s_wsum[w] = incl;
-            __syncthreads();
-            int base = incl - (c0 + c1);
-            for (int ww = 0; ww < w; ++ww) base += s_wsum[ww];
-            if (2 * tid < words) s_pref[2 * tid] = base;
-            if (2 * tid + 1 < words) s_pref[2 * tid + 1] = base + c0;
-            if (tid == kEdgeThreads - 1) s_total = base + c0 + c1;
-            // the rows themselves, in slot order (only meaningful when they fit; harmless otherwise: bounded by cap)
-            int at = base;
-            unsigned m = b0;
-            while (m) { const int bit = __ffs(m) - 1; m &= m - 1; if (at < cap) s_uid[at] = (2 * tid) * 32 + bit; ++at; }
-            m = b1;
-            while (m) { const int bit = __ffs(m) - 1; m &= m - 1; if (at < cap) s_uid[at] = (2 * tid + 1) * 32 + bit; ++at; }
-        }
-        __syncthreads();
-        const int total = s_total;
-        const bool in_smem = total <= cap;
-        if (in_smem) {   // copy the referenced rows: a warp per row, 8 bytes per lane and channel pair
-            for (int u = w; u < total; u += nwarps) {
-                const float* row = P + (size_t)s_uid[u] * C;
-#pragma unroll
-                for (int q = 0; q < PAIRS; ++q)
-                    if (on[q]) *reinterpret_cast<float2*>(s_tab + (size_t)u * C + coff[q]) = __ldg(reinterpret_cast<const float2*>(row + coff[q]));
-            }
-        }
-        __syncthreads();
-        // ---- the edge stage of the tile's points: warp w takes points w, w + 8, ... ----
-        for (int pi = w; pi < kTileP; pi += nwarps) {
-            const int i = __ldg(order + r0 + pi);
-            const long long pt = (long long)b * N + i;
-            const float* ef = edge_feats + ((size_t)pt * 32 + lane) * 3;
-            const int id = __ldg(nbr + pt * 32 + lane);
-            // where neighbour `lane` lives: its slot in the shared-memory table, or its row in global memory
-            const int slot = s_pref[id >> 5] + __popc(s_bits[id >> 5] & ((1u << (id & 31)) - 1u));
-            __syncwarp();
-            s_edge[w * 32 + lane] = make_float4(__int_as_float((in_smem ? slot : id) * C), __ldg(ef), __ldg(ef + 1), __ldg(ef + 2));
-            __syncwarp();
-            unsigned long long pc[PAIRS], s1[PAIRS], s2[PAIRS];
-            float2 mx[PAIRS], mn[PAIRS];
-#pragma unroll
-            for (int q = 0; q < PAIRS; ++q) {
-                const float2 tt = __ldg(reinterpret_cast<const float2*>(P + (size_t)i * C + coff[q]));
-                pc[q] = pk(tt.x, tt.y);
-                mx[q] = make_float2(-INFINITY, -INFINITY); mn[q] = make_float2(INFINITY, INFINITY);
-                s1[q] = pk(0.f, 0.f); s2[q] = pk(0.f, 0.f);
-            }
-            // (two copies of the loop so that the common one reads the table with shared-memory loads, not generic ones)
-#define PVRAFT_EDGE_LOOP(ROWPTR, LOAD)                                                                              \
-            _Pragma("unroll 8") for (int e = 0; e < 32; ++e) {                                                      \
-                const float4 ed = s_edge[w * 32 + e];                                                               \
-                const float* row = (ROWPTR) + __float_as_int(ed.x);                                                 \
-                const unsigned long long ex = pk(ed.y, ed.y), ey = pk(ed.z, ed.z), ez = pk(ed.w, ed.w);             \
-                _Pragma("unroll") for (int q = 0; q < PAIRS; ++q) {                                                 \
-                    const float2 pj = LOAD(reinterpret_cast<const float2*>(row + coff[q]));                         \
-                    const unsigned long long tq = fma2(wz2[q], ez, fma2(wy2[q], ey, mul2(wx2[q], ex)));             \
-                    const unsigned long long y2 = add2(sub2(pk(pj.x, pj.y), pc[q]), tq);                            \
-                    const float2 y = upk(y2);                                                                       \
-                    mx[q].x = fmaxf(mx[q].x, y.x); mx[q].y = fmaxf(mx[q].y, y.y);                                   \
-                    mn[q].x = fminf(mn[q].x, y.x); mn[q].y = fminf(mn[q].y, y.y);                                   \
-                    s1[q] = add2(s1[q], y2);                                                                        \
-                    s2[q] = fma2(y2, y2, s2[q]);                                                                    \
-                }                                                                                                   \
-            }
-#define PVRAFT_LD_SHARED(p) (*(p))
-            if (in_smem) { PVRAFT_EDGE_LOOP(s_tab, PVRAFT_LD_SHARED) } else { PVRAFT_EDGE_LOOP(P, __ldg) }
-#undef PVRAFT_EDGE_LOOP
-#undef PVRAFT_LD_SHARED
-#pragma unroll
-            for (int q = 0; q < PAIRS; ++q) {
-                const size_t o = (size_t)pt * C + coff[q];
-                if (on[q]) {
-                    *reinterpret_cast<float2*>(ymax + o) = mx[q];
-                    *reinterpret_cast<float2*>(ymin + o) = mn[q];
-                }
-                const float2 a1 = upk(s1[q]), a2 = upk(s2[q]);
-                dS[q][0] += (double)a1.x; dS[q][1] += (double)a1.y;
-                dSS[q][0] += (double)a2.x; dSS[q][1] += (double)a2.y;
-            }
-        }
-    }
-    if (cur_b >= 0) flush(cur_b);
-}
-
 }  // namespace pvraft
 
 using namespace pvraft;
@@ -365,23 +176,6 @@ extern "C" int pvraft_setconv_edge_fwd(const float* fc1p, const int32_t* nbr, co
     if (g > need) g = need;
     const int grid = (int)(g < 1 ? 1 : g);
     cudaStream_t st = (cudaStream_t)stream;
-    static const bool tiled_on = []() { const char* e = getenv("PVRAFT_EDGE_TILED"); return !(e && atoi(e) == 0); }();
-    if (tiled_on && order && N % kTileP == 0 && N <= 16384) {
-        // shared-memory row table: spatially coherent tiles of 32 points gather their (few hundred) distinct neighbour rows once
-        const size_t smem = (size_t)kTabBytes + 512 * 4 + 512 * 4 + 1280 * 4 + 8 * 32 * 16 + 8 * 128 * 2 * 8;
-        const long long n_tiles = total / kTileP;
-        long long gt = (long long)sm_count() * 2;
-        if (gt > n_tiles) gt = n_tiles;
-        int rc;
-        if (C <= 64) {
-            if ((rc = opt_in_smem(k_setconv_edge_tiled<1>, smem))) return rc;
-            launch_pdl(k_setconv_edge_tiled<1>, (int)gt, kEdgeThreads, smem, st, fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats, order);
-        } else {
-            if ((rc = opt_in_smem(k_setconv_edge_tiled<2>, smem))) return rc;
-            launch_pdl(k_setconv_edge_tiled<2>, (int)gt, kEdgeThreads, smem, st, fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats, order);
-        }
-        return check_launch("setconv_edge");
-    }
     if (C <= 64) {
         launch_pdl(k_setconv_edge_pairs<1>, grid, kEdgeThreads, 0, st, fc1p, nbr, edge_feats, w_fc1, cin, B, N, C, ymax, ymin, stats, order);
         return check_launch("setconv_edge");
