@@ -427,6 +427,35 @@ def run_train(a):
 
     for _ in range(max(a.warmup, 3)):
         step_resident()
+    graphed = False
+    if a.graph and world == 1:
+        # whole-step CUDA graph (forward + backward + Adam): the eager step is bound by the host launch path (~660 library
+        # launches + ATen glue per step); replaying one graph shows what the kernels themselves take
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step_resident()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        launches_per_step = [0]
+        g = torch.cuda.CUDAGraph()
+        l0 = ops.launch_count
+        with torch.cuda.graph(g):
+            step_resident()
+        launches_per_step[0] = ops.launch_count - l0
+
+        def step_resident():   # noqa: F811
+            g.replay()
+            ops.launch_count += launches_per_step[0]
+
+        def step_e2e():   # noqa: F811
+            pc1.copy_(pc1_h, non_blocking=True)
+            pc2.copy_(pc2_h, non_blocking=True)
+            step_resident()
+        graphed = True
+        for _ in range(3):
+            step_resident()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -457,7 +486,8 @@ def run_train(a):
         'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3), 'ms_per_step': ms / a.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': f'training step (forward + backward + Adam) of RSF: N={N_POINTS} pts x2 clouds, truncate_k={TRUNC_K}, '
-                               f'iters={iters}, batch {B}/GPU, fp32 (BASELINE.json configs[3])', 'global_batch': gb, 'points': N_POINTS,
+                               f'iters={iters}, batch {B}/GPU, fp32 (BASELINE.json configs[3])' + (', whole step replayed as one CUDA graph' if graphed else ''),
+                   'global_batch': gb, 'points': N_POINTS,
                    'truncate_k': TRUNC_K, 'iters': iters,
                    'parallelism': f'DDP batch-shard x{world}: one gradient all-reduce of {nparam * 4} B per step (NCCL)'},
         'e2e': {'value': gb * iters * a.steps / (ms_e2e * 1e-3), 'unit': 'sample-iterations/s',
