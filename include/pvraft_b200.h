@@ -229,7 +229,9 @@ PVRAFT_API int pvraft_tc_weight_split(const float* w, int rows, int cols, int ld
 /* out[B,N,C] (or channel-major [B,C,N] when transpose_out != 0) = act(GN(in)) -- the trailing
  * GroupNorm+LeakyReLU of SetConv (model/flot/gconv.py:33,82-83) when nothing follows it. */
 PVRAFT_API int pvraft_gn_act_fwd(const float* in, const double* stats, const float* gamma, const float* beta, double count,
-                      int act, float slope, int B, int N, int C, int transpose_out, float* out, void* stream);
+                      int act, float slope, int B, int N, int C, int transpose_out, float* out, const float* slope_dev, void* stream);
+/* slope_dev (here and in pvraft_gn_act_bwd): optional DEVICE pointer to the slope -- the one-element nn.PReLU weight -- read by the
+ * kernel instead of `slope`; the training path uses it so that a parameter the optimizer changes every step needs no host read-back. */
 
 /* ------------------------------------------------------------------------------------------------
  * Correlation feature head (+ optional MotionEncoder), one persistent kernel.
@@ -394,7 +396,7 @@ PVRAFT_API int pvraft_linear_wgrad(const float* x, const float* dy, int64_t rows
  *      gsum [B,8,2] double scratch, ZEROED by the caller. */
 PVRAFT_API int pvraft_gn_act_bwd(const float* x, const float* dy, const double* stats, const float* gamma, const float* beta, double count,
                       int act, float slope, int B, int64_t rows, int C, double* gsum, double* dgamma, double* dbeta, double* dslope,
-                      float* dx, void* stream);
+                      float* dx, const float* slope_dev, void* stream);
 
 /* SetConv edge stage, layer-wise (model/flot/gconv.py:65-73, fc1 factorised as in pvraft_setconv_edge_fwd):
  *   forward : E[b,n,j,:] <- P[b,nbr[b,n,j],:] - P[b,n,:] + E[b,n,j,:]  (in place; E = W_e . edge_feats from pvraft_linear_fwd),

@@ -217,7 +217,8 @@ __global__ void __launch_bounds__(kMlpThreads, 2) k_linear(const LinearParams P)
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_gn_act(const float* __restrict__ in, const double* __restrict__ stats, const float* __restrict__ gamma,
                          const float* __restrict__ beta, double count, int act, float slope, int B, int N, int C,
-                         int transpose_out, float* __restrict__ out) {
+                         int transpose_out, float* __restrict__ out, const float* __restrict__ slope_dev) {
+    if (slope_dev) slope = __ldg(slope_dev);   // a learnable PReLU slope read on the device (no host read-back per optimizer step)
     __shared__ float s_scale[256], s_shift[256];
     __shared__ float s_tile[32][33];
     const int b = blockIdx.z;
@@ -747,11 +748,12 @@ extern "C" int pvraft_linear_fwd(const pvraft_linear_args* a, void* stream) {
 }
 
 extern "C" int pvraft_gn_act_fwd(const float* in, const double* stats, const float* gamma, const float* beta, double count,
-                                 int act, float slope, int B, int N, int C, int transpose_out, float* out, void* stream) {
+                                 int act, float slope, int B, int N, int C, int transpose_out, float* out, const float* slope_dev,
+                                 void* stream) {
     if (!in || !stats || !gamma || !beta || !out) return fail(PVRAFT_ERR_BAD_ARG, "gn_act: null pointer");
     if (C > 256 || C % PVRAFT_GN_GROUPS) return fail(PVRAFT_ERR_UNSUPPORTED, "gn_act: C=%d", C);
     dim3 grid((N + 31) / 32, (C + 31) / 32, B), block(32, 8);
-    k_gn_act<<<grid, block, 0, (cudaStream_t)stream>>>(in, stats, gamma, beta, count, act, slope, B, N, C, transpose_out, out);
+    k_gn_act<<<grid, block, 0, (cudaStream_t)stream>>>(in, stats, gamma, beta, count, act, slope, B, N, C, transpose_out, out, slope_dev);
     return check_launch("gn_act");
 }
 

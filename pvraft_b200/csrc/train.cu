@@ -119,6 +119,7 @@ struct GnBwdParams {
     double* dbeta;         // [C]
     double* dslope;        // [1] or null
     float* dx;
+    const float* slope_dev;   // device copy of the slope (PReLU weight) or null
 };
 
 __device__ __forceinline__ void gn_mean_rstd(const double* st, double count, float& mean, float& rstd) {
@@ -129,7 +130,9 @@ __device__ __forceinline__ void gn_mean_rstd(const double* st, double count, flo
     rstd = (float)rsqrt(var + 1e-5);
 }
 
-__global__ void __launch_bounds__(256) k_gn_bwd_reduce(const GnBwdParams p) {
+__global__ void __launch_bounds__(256) k_gn_bwd_reduce(const GnBwdParams pp) {
+    GnBwdParams p = pp;
+    if (p.slope_dev) p.slope = __ldg(p.slope_dev);
     __shared__ double s_g[8][2];
     __shared__ double s_par[3];   // unused slots keep the layout simple
     const int b = blockIdx.y;
@@ -176,7 +179,9 @@ __global__ void __launch_bounds__(256) k_gn_bwd_reduce(const GnBwdParams p) {
     if (threadIdx.x == 0 && p.dslope && s_par[0] != 0.0) atomicAdd(p.dslope, s_par[0]);
 }
 
-__global__ void __launch_bounds__(256) k_gn_bwd_apply(const GnBwdParams p) {
+__global__ void __launch_bounds__(256) k_gn_bwd_apply(const GnBwdParams pp) {
+    GnBwdParams p = pp;
+    if (p.slope_dev) p.slope = __ldg(p.slope_dev);
     const int b = blockIdx.y;
     const int C = p.C, gsz = C / PVRAFT_GN_GROUPS;
     const int rpp = blockDim.x / C;
@@ -433,10 +438,10 @@ extern "C" int pvraft_linear_wgrad(const float* x, const float* dy, int64_t rows
 
 extern "C" int pvraft_gn_act_bwd(const float* x, const float* dy, const double* stats, const float* gamma, const float* beta, double count,
                                  int act, float slope, int B, int64_t rows, int C, double* gsum, double* dgamma, double* dbeta,
-                                 double* dslope, float* dx, void* stream) {
+                                 double* dslope, float* dx, const float* slope_dev, void* stream) {
     if (!x || !dy || !stats || !gamma || !beta || !gsum || !dgamma || !dbeta || !dx) return fail(PVRAFT_ERR_BAD_ARG, "gn_act_bwd: null pointer");
     if (C > 256 || C % PVRAFT_GN_GROUPS || B <= 0 || rows <= 0) return fail(PVRAFT_ERR_UNSUPPORTED, "gn_act_bwd: C=%d", C);
-    GnBwdParams p{x, dy, stats, gamma, beta, count, act, slope, (long long)rows, B, C, gsum, dgamma, dbeta, dslope, dx};
+    GnBwdParams p{x, dy, stats, gamma, beta, count, act, slope, (long long)rows, B, C, gsum, dgamma, dbeta, dslope, dx, slope_dev};
     const int rpp = 256 / C;
     long long workers = (rows + rpp - 1) / rpp;
     const long long cap = ((long long)sm_count() * 8 + B - 1) / B;

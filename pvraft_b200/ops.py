@@ -294,11 +294,12 @@ def tc_linear(sources, w, bias=None, *, in_min=None, in_stats=None, in_gamma=Non
     return out
 
 
-def gn_act(x, stats, gamma, beta, count, act=ACT_LRELU, slope=0.1, transpose_out=False):
+def gn_act(x, stats, gamma, beta, count, act=ACT_LRELU, slope=0.1, transpose_out=False, slope_dev=None):
+    """slope_dev: optional one-element device tensor (a PReLU weight) the kernel reads instead of the scalar `slope`."""
     b, n, c = x.shape
     out = torch.empty((b, c, n) if transpose_out else (b, n, c), dtype=torch.float32, device=x.device)
     _count(lib().pvraft_gn_act_fwd(_p(x), _p(stats, torch.float64), _p(gamma), _p(beta), float(count), act, float(slope),
-                                   b, n, c, int(transpose_out), _p(out), _stream()), 'gn_act')
+                                   b, n, c, int(transpose_out), _p(out), _p(slope_dev), _stream()), 'gn_act')
     return out
 
 
@@ -359,7 +360,7 @@ def linear_wgrad(x, dy, dw, db=None):
            'linear_wgrad')
 
 
-def gn_act_bwd(x, dy, stats, gamma, beta, count, act, slope, want_dslope=False):
+def gn_act_bwd(x, dy, stats, gamma, beta, count, act, slope, want_dslope=False, slope_dev=None):
     """-> (dx, dgamma [C] f32, dbeta [C] f32, dslope [1] f32 or None)."""
     b, rows, c = x.shape
     dev = x.device
@@ -368,7 +369,7 @@ def gn_act_bwd(x, dy, stats, gamma, beta, count, act, slope, want_dslope=False):
     dx = torch.empty_like(x)
     _count(lib().pvraft_gn_act_bwd(_p(x), _p(dy), _p(stats, torch.float64), _p(gamma), _p(beta), float(count), act, float(slope), b, rows,
                                    c, gsum.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), dslope.data_ptr() if want_dslope else None,
-                                   _p(dx), _stream()), 'gn_act_bwd')
+                                   _p(dx), _p(slope_dev), _stream()), 'gn_act_bwd')
     return dx, dgamma.float(), dbeta.float(), (dslope.float() if want_dslope else None)
 
 

@@ -78,22 +78,24 @@ class GnActFn(torch.autograd.Function):
         b, rows, c = x.shape
         count = float(rows) * (c // 8)
         x = x.contiguous()
-        y = ops.gn_act(x, stats, gamma.detach(), beta.detach(), count, act, slope)
-        ctx.save_for_backward(x, stats, gamma.detach(), beta.detach())
+        sdev = None if slope_param is None else slope_param.detach().reshape(-1).contiguous()   # read on the device: no host sync
+        y = ops.gn_act(x, stats, gamma.detach(), beta.detach(), count, act, slope, slope_dev=sdev)
+        ctx.save_for_backward(x, stats, gamma.detach(), beta.detach(), *(() if sdev is None else (sdev,)))
         ctx.cfg = (count, act, float(slope), slope_param is not None, None if slope_param is None else slope_param.shape)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, stats, gamma, beta = ctx.saved_tensors
+        x, stats, gamma, beta = ctx.saved_tensors[:4]
         count, act, slope, has_slope, slope_shape = ctx.cfg
-        dx, dgamma, dbeta, dslope = ops.gn_act_bwd(x, dy.contiguous(), stats, gamma, beta, count, act, slope, has_slope)
+        sdev = ctx.saved_tensors[4] if has_slope else None
+        dx, dgamma, dbeta, dslope = ops.gn_act_bwd(x, dy.contiguous(), stats, gamma, beta, count, act, slope, has_slope, slope_dev=sdev)
         return dx, None, dgamma, dbeta, (dslope.reshape(slope_shape) if has_slope else None), None, None
 
 
 def gn_act(x, stats, gn, act=ACT_LRELU, slope=0.1, prelu=None):
-    if prelu is not None:   # the kernels take the slope as a scalar: read back once per parameter version
-        slope = ops.derived((prelu.weight,), 'slope', lambda w: float(w.detach().reshape(-1)[0]))
+    """prelu: an nn.PReLU whose one-element weight is the slope -- handed to the kernels as a device pointer (the optimizer
+    changes it every step; a host read-back would synchronise the stream twice per RAFT iteration)."""
     return GnActFn.apply(x, stats, gn.weight, gn.bias, None if prelu is None else prelu.weight, act, slope)
 
 
