@@ -140,10 +140,8 @@ class _RaftBase(nn.Module):
         preds = []
         me = self.update_block.motion_encoder
         use_tc = ops.tc_supported(n)
-        # (ConvGRU.context_terms -- the constant context part of the gate pre-activations hoisted out of the loop, K = 128
-        #  per iteration -- was measured slower, 22.15 vs 21.72 ms per forward: the two extra per-point reads outweigh the
-        #  shorter GEMM; the loop keeps the K = 192 form)
-        self._gru_pre = None
+        # (hoisting the constant context part of the GRU pre-activations out of the loop -- K = 128 per iteration instead of 192 --
+        #  was measured slower in round 1, 22.15 vs 21.72 ms per forward: the two extra per-point reads outweigh the shorter GEMM)
         with ops.stats_arena(b, xyz1.device, 5 * num_iters):   # moments + 4 GroupNorm accumulators per iteration, one memset
             return self._iterate_body(xyz1, graph_context, net, inp, num_iters, keep_all, coords2, flow, preds, me, use_tc)
 
@@ -163,7 +161,7 @@ class _RaftBase(nn.Module):
                 _, keep = self.corr_block.feature_point_major(coords2, motion_args=attach)   # :42 + update.py:83
             new_flow = torch.empty_like(xyz1)
             user_flow = torch.empty_like(xyz1) if (keep_all and self._row_map is not None) else None   # caller's point order
-            net, _ = self.update_block.forward_pm(net, inp, motion, graph_context, gru_pre=self._gru_pre, coords1=xyz1, coords2=coords2,
+            net, _ = self.update_block.forward_pm(net, inp, motion, graph_context, coords1=xyz1, coords2=coords2,
                                                   coords2_out=coords2, flow_out=new_flow, flow_user=user_flow,
                                                   row_map=self._row_map if user_flow is not None else None)   # :44-46
             flow = new_flow

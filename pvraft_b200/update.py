@@ -64,33 +64,10 @@ class ConvGRU(nn.Module):
         self.convr = nn.Conv1d(input_dim + hidden_dim, hidden_dim, 1)
         self.convq = nn.Conv1d(input_dim + hidden_dim, hidden_dim, 1)
 
-    def context_terms(self, inp):
-        """The part of the gate pre-activations that depends only on the context features `inp` (constant over the RAFT
-        iterations, model/RAFTSceneFlow.py:33-35 vs update.py:32-36): ([B,N,128] = [z|r], [B,N,64] = q), biases included.
-        Computed once per forward; the per-iteration GEMMs then run over K = 128 instead of 192."""
-        bias_zr = ops.derived((self.convz.bias, self.convr.bias), 'cat', lambda x, y: torch.cat([x.detach(), y.detach()]).contiguous())
-        pre_zr = ops.tc_linear([inp], ops.tc_weights((self.convz.weight, self.convr.weight), col0=64, cols=64), bias_zr)
-        pre_q = ops.tc_linear([inp], ops.tc_weights(self.convq.weight, col0=64, cols=64), _w(self.convq.bias))
-        return pre_zr, pre_q
-
-    def forward_pm(self, net, inp, motion, out=None, pre=None):
+    def forward_pm(self, net, inp, motion, out=None):
         b, n, _ = net.shape
         if out is None:
             out = torch.empty_like(net)
-        if ops.tc_supported(n) and pre is not None:
-            # [z|r] = sigmoid(W_h h + W_m motion + pre_zr); q = tanh(W_h (r*h) + W_m motion + pre_q)   (update.py:32-39)
-            def drop_inp(*ws):   # columns [h | motion] of the [h | inp | motion] weights
-                return torch.cat([torch.cat([w.detach().reshape(w.shape[0], -1)[:, :64], w.detach().reshape(w.shape[0], -1)[:, 128:]], 1)
-                                  for w in ws], 0).contiguous()
-
-            w_zr = ops.derived((self.convz.weight, self.convr.weight), 'gru_hm', drop_inp)
-            w_q = ops.derived((self.convq.weight,), 'gru_hm', drop_inp)
-            z, rh = torch.empty_like(net), torch.empty_like(net)
-            ops.tc_linear([net, motion], ops.tc_weights(w_zr), None, residual=pre[0], epilogue=ops.TC_GRU_ZR, out=z, out2=rh,
-                          h=net, cout=64)
-            ops.tc_linear([rh, motion], ops.tc_weights(w_q), None, residual=pre[1], epilogue=ops.TC_GRU_Q, out=out, h=net,
-                          z=z, cout=64)
-            return out
         if ops.tc_supported(n):
             # tcgen05: [z|r] = sigmoid(W_zr [h,x]); q = tanh(W_q [r*h, x]); h' = (1-z) h + z q   (update.py:32-39)
             z, rh = torch.empty_like(net), torch.empty_like(net)
@@ -174,8 +151,8 @@ class UpdateBlock(nn.Module):
         self.gru = ConvGRU(input_dim=input_dim, hidden_dim=hidden_dim)
         self.flow_head = FlowHead(input_dim=hidden_dim)
 
-    def forward_pm(self, net, inp, motion, graph, gru_pre=None, **coords):
-        net = self.gru.forward_pm(net, inp, motion, pre=gru_pre)
+    def forward_pm(self, net, inp, motion, graph, **coords):
+        net = self.gru.forward_pm(net, inp, motion)
         delta = self.flow_head.forward_pm(net, graph, **coords)
         return net, delta
 

@@ -501,18 +501,6 @@ def test_cuda_graph_replay_matches_eager(dev):
     assert rel_err(again.cpu(), eager[0].cpu()) < 1e-6
 
 
-def test_gru_context_terms_match_full_gemm(dev):
-    """ConvGRU with the context part of the pre-activations precomputed (K = 128 per iteration) == the K = 192 form."""
-    from pvraft_b200.update import ConvGRU
-    torch.manual_seed(3)
-    gru = ConvGRU().to(dev).eval()
-    net, inp, motion = [torch.randn(2, 256, 64, device=dev) for _ in range(3)]
-    with torch.no_grad():
-        full = gru.forward_pm(net, inp, motion)
-        fast = gru.forward_pm(net, inp, motion, pre=gru.context_terms(inp))
-    assert rel_err(fast.cpu(), full.cpu()) < 1e-5
-
-
 @pytest.mark.parametrize('refine', [False, True])
 def test_internal_point_reordering_is_invisible(dev, refine):
     """RSF / RSF_refine Morton-order the first cloud internally: the returned flows are in the caller's order and agree with
