@@ -183,6 +183,38 @@ def gpu_reference_sample(dev, batch, iters):
         torch.cuda.empty_cache()
 
 
+def gpu_reference_train_sample(dev, batch, iters):
+    """One training step (forward + backward through torch autograd + Adam) of the reference's op sequence on `dev`, as
+    gpu_reference_sample: fp32, TF32 off, one warm-up step then one timed step; returns seconds."""
+    from oracle import pvraft_oracle as O
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        W = {k: v.to(dev).requires_grad_(True) for k, v in _cpu_weights().items()}
+        opt = torch.optim.Adam(list(W.values()), lr=1e-3)
+        pc1, pc2 = [t.to(dev) for t in synthetic_clouds(batch, N_POINTS, 1234)]
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            flows = O.rsf_forward(W, pc1, pc2, iters, LEVELS, BASE_SCALE, TRUNC_K)
+            n = len(flows)
+            sum(0.8 ** (n - i - 1) * (flows[i] - (pc2 - pc1)).abs().sum(-1).mean() for i in range(n)).backward()
+            opt.step()
+
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        torch.cuda.empty_cache()
+
+
 def run_reference(a):
     """`--impl reference`: the reference's CPU formulation (oracle port; the reference itself is pure PyTorch and is not present on
     the GPU box) timed on the host cores, same metric / unit / config.  A step is ONE full forward at B=1: the pre-loop work
@@ -481,6 +513,16 @@ def run_train(a):
     if rank != 0:
         return None
     gb = B * world
+    gpu_ref = None
+    if world == 1 and not a.no_gpu_ref:
+        try:
+            t_ref = gpu_reference_train_sample(dev, B, iters)
+            gpu_ref = {'value': B * iters / t_ref, 'unit': 'sample-iterations/s', 'ms_per_step': 1e3 * t_ref,
+                       'kind': "the reference's own op sequence (oracle port of model/*.py) with torch autograd + Adam in torch eager "
+                               f'on this GPU, fp32, TF32 off, batch {B}, {iters} iterations, one timed step after a warm-up step',
+                       'speedup': (gb * iters * a.steps / (ms * 1e-3)) / (B * iters / t_ref)}
+        except Exception as e:   # noqa: BLE001
+            gpu_ref = {'unavailable': f'{type(e).__name__}: {e}'[:200]}
     return {
         'metric': 'raft_train_sample_iters_per_sec', 'value': gb * iters * a.steps / (ms * 1e-3), 'unit': 'sample-iterations/s',
         'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3), 'ms_per_step': ms / a.steps, 'higher_is_better': True,
@@ -492,7 +534,7 @@ def run_train(a):
                    'parallelism': f'DDP batch-shard x{world}: one gradient all-reduce of {nparam * 4} B per step (NCCL)'},
         'e2e': {'value': gb * iters * a.steps / (ms_e2e * 1e-3), 'unit': 'sample-iterations/s',
                 'h2d_bytes_per_step': 2 * B * N_POINTS * 3 * 4 * world, 'd2h_bytes_per_step': 4 * world, 'ms_per_step': ms_e2e / a.steps},
-        'gpu_launches': launches, 'clocks': clocks, 'collective': coll,
+        'gpu_launches': launches, 'clocks': clocks, 'collective': coll, 'gpu_reference': gpu_ref,
     }
 
 

@@ -396,7 +396,16 @@ PVRAFT_API int pvraft_linear_wgrad(const float* x, const float* dy, int64_t rows
  *      gsum [B,8,2] double scratch, ZEROED by the caller. */
 PVRAFT_API int pvraft_gn_act_bwd(const float* x, const float* dy, const double* stats, const float* gamma, const float* beta, double count,
                       int act, float slope, int B, int64_t rows, int C, double* gsum, double* dgamma, double* dbeta, double* dslope,
-                      float* dx, const float* slope_dev, void* stream);
+                      float* dx, const float* slope_dev, const uint8_t* arg, void* stream);
+/* Backward of a linear layer with cin <= 4 and cout in {32,64,128} (the SetConv edge term and the knn_conv: rows = B*N*32) in one
+ * pass over dy: dW [cout,dw_ld] += dy^T x, db [cout] += column sums (or NULL), dx [rows,cin] = dy W (or NULL).  W is [cout,w_ld]. */
+PVRAFT_API int pvraft_linear_bwd_small(const float* x, const float* dy, const float* W, int64_t rows, int cin, int cout, int w_ld, float* dW,
+                            int dw_ld, float* db, float* dx, void* stream);
+/* GroupNorm + activation + max over each point's 32 consecutive rows, fused (model/flot/gconv.py:76-80, model/corr.py:87-92):
+ *   x [B, pts*32, C] -> y [B,pts,C], arg [B,pts,C] uint8 (first row attaining the maximum); count = pts*32 * C/8.
+ * Its backward is pvraft_gn_act_bwd with `arg` set and dy = d y [B,pts,C]: the dense, 31/32-zero gradient of the max is never formed. */
+PVRAFT_API int pvraft_gn_act_maxk_fwd(const float* x, const double* stats, const float* gamma, const float* beta, double count, int act,
+                           float slope, int B, int64_t pts_per_sample, int C, float* y, uint8_t* arg, const float* slope_dev, void* stream);
 
 /* SetConv edge stage, layer-wise (model/flot/gconv.py:65-73, fc1 factorised as in pvraft_setconv_edge_fwd):
  *   forward : E[b,n,j,:] <- P[b,nbr[b,n,j],:] - P[b,n,:] + E[b,n,j,:]  (in place; E = W_e . edge_feats from pvraft_linear_fwd),

@@ -96,6 +96,111 @@ __global__ void __launch_bounds__(kWgThreads) k_linear_wgrad(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Backward of a linear layer with a tiny input width (cin <= 4: the SetConv edge term W_e e over [dx,dy,dz] and the
+// knn_conv over [corr, dx, dy, dz]; rows = B*N*32).  ONE pass over dy [rows, cout] gives dW, db and (if asked) dx -- the
+// generic pair (k_linear with the transposed weight + k_linear_wgrad) reads dy twice and keeps 8 of 256 threads busy in
+// the weight-gradient tile loop at this shape.  LPR lanes share a row, 16 output channels each (cout = 16 * LPR).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int LPR>
+__global__ void __launch_bounds__(256) k_linear_bwd_small(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ W,
+                                                          long long rows, int cin, int w_ld, float* __restrict__ dW, int dw_ld,
+                                                          float* __restrict__ db, float* __restrict__ dx) {
+    constexpr int COUT = 16 * LPR, RPW = 32 / LPR;
+    __shared__ float4 s_w[COUT];
+    __shared__ float s_acc[COUT][5];
+    const int lane = lane_id(), w = warp_id(), q = lane % LPR, rr = lane / LPR;
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < cin; ++k) v[k] = __ldg(W + (size_t)i * w_ld + k);
+        s_w[i] = make_float4(v[0], v[1], v[2], v[3]);
+        for (int k = 0; k < 5; ++k) s_acc[i][k] = 0.f;
+    }
+    __syncthreads();
+    float acc[16][4], accb[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) { accb[o] = 0.f; acc[o][0] = acc[o][1] = acc[o][2] = acc[o][3] = 0.f; }
+    const long long stride = (long long)gridDim.x * 8 * RPW;
+    long long r = ((long long)blockIdx.x * 8 + w) * RPW + rr;
+    float4 d4[4];
+    float xv[4];
+    auto fetch = [&](long long row) {
+        if (row < rows) {
+            const float4* dp = reinterpret_cast<const float4*>(dy + (size_t)row * COUT + q * 16);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) d4[k] = __ldg(dp + k);
+            if (cin == 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(x + (size_t)row * 4));
+                xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xv[k] = k < cin ? __ldg(x + (size_t)row * cin + k) : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { d4[k] = make_float4(0.f, 0.f, 0.f, 0.f); xv[k] = 0.f; }
+        }
+    };
+    fetch(r);
+    // every lane of a warp runs the same number of passes (the dx reduction below shuffles across the row's lanes)
+    const long long r_warp = ((long long)blockIdx.x * 8 + w) * RPW;
+    for (long long rw = r_warp; rw < rows; rw += stride, r += stride) {
+        const float d[16] = {d4[0].x, d4[0].y, d4[0].z, d4[0].w, d4[1].x, d4[1].y, d4[1].z, d4[1].w,
+                             d4[2].x, d4[2].y, d4[2].z, d4[2].w, d4[3].x, d4[3].y, d4[3].z, d4[3].w};
+        const float xc[4] = {xv[0], xv[1], xv[2], xv[3]};
+        fetch(r + stride);   // next pass in flight while this one is consumed
+        float sx[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+            accb[o] += d[o];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[o][k] = fmaf(d[o], xc[k], acc[o][k]);
+            if (dx) {
+                const float4 wv = s_w[q * 16 + o];
+                sx[0] = fmaf(d[o], wv.x, sx[0]); sx[1] = fmaf(d[o], wv.y, sx[1]);
+                sx[2] = fmaf(d[o], wv.z, sx[2]); sx[3] = fmaf(d[o], wv.w, sx[3]);
+            }
+        }
+        if (dx) {
+#pragma unroll
+            for (int m = 1; m < LPR; m <<= 1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) sx[k] += __shfl_xor_sync(0xffffffffu, sx[k], m);
+            }
+            if (q == 0 && r < rows) {
+                if (cin == 4) {
+                    *reinterpret_cast<float4*>(dx + (size_t)r * 4) = make_float4(sx[0], sx[1], sx[2], sx[3]);
+                } else {
+                    for (int k = 0; k < cin; ++k) dx[(size_t)r * cin + k] = sx[k];
+                }
+            }
+        }
+    }
+    // rows of the warp -> lanes rr == 0, then the CTA's 8 warps -> shared -> one global atomic per entry
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+#pragma unroll
+        for (int m = LPR; m < 32; m <<= 1) {
+            accb[o] += __shfl_xor_sync(0xffffffffu, accb[o], m);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[o][k] += __shfl_xor_sync(0xffffffffu, acc[o][k], m);
+        }
+        if (rr == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) atomicAdd(&s_acc[q * 16 + o][k], acc[o][k]);
+            atomicAdd(&s_acc[q * 16 + o][4], accb[o]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < COUT * 5; i += blockDim.x) {
+        const int o = i / 5, k = i - o * 5;
+        const float v = s_acc[o][k];
+        if (v == 0.f) continue;
+        if (k < 4) { if (k < cin) atomicAdd(dW + (size_t)o * dw_ld + k, v); }
+        else if (db) atomicAdd(db + o, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // GroupNorm(8 groups) + activation, backward.   y = act(xh * gamma + beta), xh = (x - mean) * rstd   (per sample, group)
 //   g   = dy * act'(.)                                 dgamma[c] += sum g * xh,   dbeta[c] += sum g
 //   dxh = g * gamma                                    dslope    += sum_{t<0} dy * t   (t = xh*gamma+beta; PReLU only)
@@ -120,6 +225,8 @@ struct GnBwdParams {
     double* dslope;        // [1] or null
     float* dx;
     const float* slope_dev;   // device copy of the slope (PReLU weight) or null
+    const uint8_t* arg;       // null: dy is [B,rows,C].  Else the activation was followed by a max over each point's 32 consecutive rows:
+                              // dy is [B,rows/32,C] and reaches only row (32*point + arg[point,c]) of column c
 };
 
 __device__ __forceinline__ void gn_mean_rstd(const double* st, double count, float& mean, float& rstd) {
@@ -135,6 +242,7 @@ __global__ void __launch_bounds__(256) k_gn_bwd_reduce(const GnBwdParams pp) {
     if (p.slope_dev) p.slope = __ldg(p.slope_dev);
     __shared__ double s_g[8][2];
     __shared__ double s_par[3];   // unused slots keep the layout simple
+    __shared__ double s_ch[2][256];   // dgamma | dbeta of this CTA: ONE global atomic per channel and CTA
     const int b = blockIdx.y;
     const int C = p.C, gsz = C / PVRAFT_GN_GROUPS;
     const int rpp = blockDim.x / C;   // rows per pass
@@ -142,6 +250,8 @@ __global__ void __launch_bounds__(256) k_gn_bwd_reduce(const GnBwdParams pp) {
     const bool live = rl < rpp;
     if (threadIdx.x < 16) (&s_g[0][0])[threadIdx.x] = 0.0;
     if (threadIdx.x < 3) s_par[threadIdx.x] = 0.0;
+    s_ch[0][threadIdx.x] = 0.0;
+    s_ch[1][threadIdx.x] = 0.0;
     __syncthreads();
     const int g = c / gsz;
     float mean, rstd;
@@ -167,14 +277,18 @@ __global__ void __launch_bounds__(256) k_gn_bwd_reduce(const GnBwdParams pp) {
         a0 += f0; a1 += f1; dg += fg; dbt += fb; dsl += fs;
         atomicAdd(&s_g[g][0], a0);
         atomicAdd(&s_g[g][1], a1);
-        if (dg != 0.0) atomicAdd(p.dgamma + c, dg);
-        if (dbt != 0.0) atomicAdd(p.dbeta + c, dbt);
+        atomicAdd(&s_ch[0][c], dg);
+        atomicAdd(&s_ch[1][c], dbt);
         if (p.dslope && dsl != 0.0) atomicAdd(&s_par[0], dsl);
     }
     __syncthreads();
     if (threadIdx.x < 16) {
         const double v = (&s_g[0][0])[threadIdx.x];
         if (v != 0.0) atomicAdd(p.gsum + (size_t)b * 16 + threadIdx.x, v);
+    }
+    if (threadIdx.x < C) {
+        if (s_ch[0][threadIdx.x] != 0.0) atomicAdd(p.dgamma + threadIdx.x, s_ch[0][threadIdx.x]);
+        if (s_ch[1][threadIdx.x] != 0.0) atomicAdd(p.dbeta + threadIdx.x, s_ch[1][threadIdx.x]);
     }
     if (threadIdx.x == 0 && p.dslope && s_par[0] != 0.0) atomicAdd(p.dslope, s_par[0]);
 }
@@ -203,6 +317,139 @@ __global__ void __launch_bounds__(256) k_gn_bwd_apply(const GnBwdParams pp) {
         else if (p.act == PVRAFT_ACT_LRELU) gq = t >= 0.f ? d : d * p.slope;
         p.dx[at] = rstd * (gq * ga - m0 - xh * m1);
     }
+}
+
+// The same two passes when the activation was followed by a max over each point's 32 consecutive rows (GnActMaxFn): only the
+// arg-max row of a (point, channel) carries gradient, so pass 1 gathers ONE x per (point, channel) -- 1/32 of the tensor -- and
+// pass 2 streams x -> dx in 16-byte pieces with the point's (arg, dy) held in registers across its 32 rows.
+__global__ void __launch_bounds__(256) k_gn_bwd_reduce_arg(const GnBwdParams pp) {
+    GnBwdParams p = pp;
+    if (p.slope_dev) p.slope = __ldg(p.slope_dev);
+    __shared__ double s_g[8][2];
+    __shared__ double s_par;
+    __shared__ double s_ch[2][256];
+    const int b = blockIdx.y;
+    const int C = p.C, gsz = C / PVRAFT_GN_GROUPS;
+    const int ppp = blockDim.x / C;   // points per pass
+    const int c = threadIdx.x % C, rl = threadIdx.x / C;
+    if (threadIdx.x < 16) (&s_g[0][0])[threadIdx.x] = 0.0;
+    if (threadIdx.x == 0) s_par = 0.0;
+    s_ch[0][threadIdx.x] = 0.0;
+    s_ch[1][threadIdx.x] = 0.0;
+    __syncthreads();
+    const int g = c / gsz;
+    float mean, rstd;
+    gn_mean_rstd(p.stats + ((size_t)b * 8 + g) * 2, p.count, mean, rstd);
+    const float ga = __ldg(p.gamma + c), be = __ldg(p.beta + c);
+    if (rl < ppp) {
+        double a0 = 0.0, a1 = 0.0, dg = 0.0, dbt = 0.0, dsl = 0.0;
+        float f0 = 0.f, f1 = 0.f, fg = 0.f, fb = 0.f, fs = 0.f;
+        int pend = 0;
+        const long long pts = p.rows >> 5, pbase = (long long)b * pts;
+        for (long long pt = (long long)blockIdx.x * ppp + rl; pt < pts; pt += (long long)gridDim.x * ppp) {
+            const size_t pc = (size_t)(pbase + pt) * C + c;
+            const int a = __ldg(p.arg + pc);
+            const float d = __ldg(p.dy + pc);
+            const float xh = (__ldg(p.x + ((size_t)(pbase + pt) * PVRAFT_KNN + a) * C + c) - mean) * rstd;
+            const float t = fmaf(xh, ga, be);
+            float gq = d;
+            if (p.act == PVRAFT_ACT_RELU) gq = t > 0.f ? d : 0.f;
+            else if (p.act == PVRAFT_ACT_LRELU) { gq = t >= 0.f ? d : d * p.slope; if (t < 0.f) fs += d * t; }
+            const float dxh = gq * ga;
+            f0 += dxh; f1 += dxh * xh; fg += gq * xh; fb += gq;
+            if (++pend == 32) { a0 += f0; a1 += f1; dg += fg; dbt += fb; dsl += fs; f0 = f1 = fg = fb = fs = 0.f; pend = 0; }
+        }
+        a0 += f0; a1 += f1; dg += fg; dbt += fb; dsl += fs;
+        atomicAdd(&s_g[g][0], a0);
+        atomicAdd(&s_g[g][1], a1);
+        atomicAdd(&s_ch[0][c], dg);
+        atomicAdd(&s_ch[1][c], dbt);
+        if (p.dslope && dsl != 0.0) atomicAdd(&s_par, dsl);
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        const double v = (&s_g[0][0])[threadIdx.x];
+        if (v != 0.0) atomicAdd(p.gsum + (size_t)b * 16 + threadIdx.x, v);
+    }
+    if (threadIdx.x < C) {
+        if (s_ch[0][threadIdx.x] != 0.0) atomicAdd(p.dgamma + threadIdx.x, s_ch[0][threadIdx.x]);
+        if (s_ch[1][threadIdx.x] != 0.0) atomicAdd(p.dbeta + threadIdx.x, s_ch[1][threadIdx.x]);
+    }
+    if (threadIdx.x == 0 && p.dslope && s_par != 0.0) atomicAdd(p.dslope, s_par);
+}
+
+__global__ void __launch_bounds__(256) k_gn_bwd_apply_arg(const GnBwdParams pp) {
+    GnBwdParams p = pp;
+    if (p.slope_dev) p.slope = __ldg(p.slope_dev);
+    const int b = blockIdx.y;
+    const int C = p.C, C4 = C >> 2, gsz = C / PVRAFT_GN_GROUPS;
+    const int ppp = blockDim.x / C4;
+    const int c4 = threadIdx.x % C4, rl = threadIdx.x / C4;
+    if (rl >= ppp) return;
+    float mean[4], rstd[4], ga[4], be[4], m0[4], m1[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = c4 * 4 + q, g = c / gsz;
+        gn_mean_rstd(p.stats + ((size_t)b * 8 + g) * 2, p.count, mean[q], rstd[q]);
+        ga[q] = __ldg(p.gamma + c);
+        be[q] = __ldg(p.beta + c);
+        m0[q] = (float)(p.gsum[((size_t)b * 8 + g) * 2] / p.count);
+        m1[q] = (float)(p.gsum[((size_t)b * 8 + g) * 2 + 1] / p.count);
+    }
+    const long long pts = p.rows >> 5, pbase = (long long)b * pts;
+    for (long long pt = (long long)blockIdx.x * ppp + rl; pt < pts; pt += (long long)gridDim.x * ppp) {
+        const size_t pc = (size_t)(pbase + pt) * C + c4 * 4;
+        const uchar4 a4 = __ldg(reinterpret_cast<const uchar4*>(p.arg + pc));
+        const float4 d4 = __ldg(reinterpret_cast<const float4*>(p.dy + pc));
+        const int a[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+        const float4* xp = reinterpret_cast<const float4*>(p.x + (size_t)(pbase + pt) * PVRAFT_KNN * C) + c4;
+        float4* op = reinterpret_cast<float4*>(p.dx + (size_t)(pbase + pt) * PVRAFT_KNN * C) + c4;
+#pragma unroll 8
+        for (int j = 0; j < PVRAFT_KNN; ++j) {
+            const float4 x4 = __ldg(xp + (size_t)j * C4);
+            const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+            float o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float xh = (xv[q] - mean[q]) * rstd[q];
+                const float t = fmaf(xh, ga[q], be[q]);
+                const float dd = a[q] == j ? d[q] : 0.f;
+                float gq = dd;
+                if (p.act == PVRAFT_ACT_RELU) gq = t > 0.f ? dd : 0.f;
+                else if (p.act == PVRAFT_ACT_LRELU) gq = t >= 0.f ? dd : dd * p.slope;
+                o[q] = rstd[q] * (gq * ga[q] - m0[q] - xh * m1[q]);
+            }
+            op[(size_t)j * C4] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+// GroupNorm + activation + max over each point's 32 consecutive rows in one pass (model/flot/gconv.py:76-80, model/corr.py:87-92):
+// the normalised [B,N*32,C] tensor is never written.  One thread per (point, channel); arg = first row attaining the maximum.
+__global__ void __launch_bounds__(256) k_gn_act_maxk(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, double count, int act, float slope, int B, long long pts_per_sample,
+                                                     int C, float* __restrict__ y, uint8_t* __restrict__ arg, const float* __restrict__ slope_dev) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * pts_per_sample * C) return;
+    if (slope_dev) slope = __ldg(slope_dev);
+    const long long pt = i / C;
+    const int c = (int)(i - pt * C), b = (int)(pt / pts_per_sample);
+    float mean, rstd;
+    gn_mean_rstd(stats + ((size_t)b * 8 + c / (C / PVRAFT_GN_GROUPS)) * 2, count, mean, rstd);
+    const float sc = rstd * __ldg(gamma + c), sh = __ldg(beta + c) - mean * rstd * __ldg(gamma + c);
+    const float* xp = x + (size_t)pt * PVRAFT_KNN * C + c;
+    float m = -INFINITY;
+    int a = 0;
+#pragma unroll 8
+    for (int j = 0; j < PVRAFT_KNN; ++j) {
+        float t = fmaf(__ldg(xp + (size_t)j * C), sc, sh);
+        if (act == PVRAFT_ACT_RELU) t = fmaxf(t, 0.f);
+        else if (act == PVRAFT_ACT_LRELU) t = t >= 0.f ? t : slope * t;
+        if (t > m) { m = t; a = j; }
+    }
+    y[i] = m;
+    arg[i] = (uint8_t)a;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -436,22 +683,66 @@ extern "C" int pvraft_linear_wgrad(const float* x, const float* dy, int64_t rows
     return check_launch("linear_wgrad");
 }
 
+extern "C" int pvraft_linear_bwd_small(const float* x, const float* dy, const float* W, int64_t rows, int cin, int cout, int w_ld, float* dW,
+                                       int dw_ld, float* db, float* dx, void* stream) {
+    if (!x || !dy || !W || !dW || rows <= 0) return fail(PVRAFT_ERR_BAD_ARG, "linear_bwd_small: bad argument");
+    if (cin < 1 || cin > 4 || (cout != 32 && cout != 64 && cout != 128))
+        return fail(PVRAFT_ERR_UNSUPPORTED, "linear_bwd_small: cin=%d cout=%d (cin <= 4, cout in {32,64,128})", cin, cout);
+    if ((reinterpret_cast<uintptr_t>(dy) & 15) || (cin == 4 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx)) & 15)))
+        return fail(PVRAFT_ERR_BAD_ARG, "linear_bwd_small: dy (and x, dx when cin == 4) must be 16-byte aligned");
+    const int lpr = cout / 16, rpc = 8 * (32 / lpr);
+    long long ctas = (rows + rpc - 1) / rpc;
+    const long long cap = (long long)sm_count();   // 152 registers x 256 threads: one resident CTA per SM
+    if (ctas > cap) ctas = cap;
+    const int wl = w_ld > 0 ? w_ld : cin, dl = dw_ld > 0 ? dw_ld : cin;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (lpr == 2) k_linear_bwd_small<2><<<(unsigned)ctas, 256, 0, st>>>(x, dy, W, rows, cin, wl, dW, dl, db, dx);
+    else if (lpr == 4) k_linear_bwd_small<4><<<(unsigned)ctas, 256, 0, st>>>(x, dy, W, rows, cin, wl, dW, dl, db, dx);
+    else k_linear_bwd_small<8><<<(unsigned)ctas, 256, 0, st>>>(x, dy, W, rows, cin, wl, dW, dl, db, dx);
+    return check_launch("linear_bwd_small");
+}
+
 extern "C" int pvraft_gn_act_bwd(const float* x, const float* dy, const double* stats, const float* gamma, const float* beta, double count,
                                  int act, float slope, int B, int64_t rows, int C, double* gsum, double* dgamma, double* dbeta,
-                                 double* dslope, float* dx, const float* slope_dev, void* stream) {
+                                 double* dslope, float* dx, const float* slope_dev, const uint8_t* arg, void* stream) {
     if (!x || !dy || !stats || !gamma || !beta || !gsum || !dgamma || !dbeta || !dx) return fail(PVRAFT_ERR_BAD_ARG, "gn_act_bwd: null pointer");
     if (C > 256 || C % PVRAFT_GN_GROUPS || B <= 0 || rows <= 0) return fail(PVRAFT_ERR_UNSUPPORTED, "gn_act_bwd: C=%d", C);
-    GnBwdParams p{x, dy, stats, gamma, beta, count, act, slope, (long long)rows, B, C, gsum, dgamma, dbeta, dslope, dx, slope_dev};
-    const int rpp = 256 / C;
-    long long workers = (rows + rpp - 1) / rpp;
+    if (arg && rows % PVRAFT_KNN) return fail(PVRAFT_ERR_BAD_ARG, "gn_act_bwd: the max-pooled form needs rows %% 32 == 0");
+    GnBwdParams p{x, dy, stats, gamma, beta, count, act, slope, (long long)rows, B, C, gsum, dgamma, dbeta, dslope, dx, slope_dev, arg};
     const long long cap = ((long long)sm_count() * 8 + B - 1) / B;
+    if (arg) {
+        const long long pts = rows / PVRAFT_KNN;
+        const int ppp_r = 256 / C, ppp_a = 256 / (C / 4);
+        long long wr = (pts + ppp_r * 16 - 1) / (ppp_r * 16), wa = (pts + ppp_a - 1) / ppp_a;   // >= 16 points per reducing thread
+        if (wr > cap) wr = cap;
+        if (wa > cap) wa = cap;
+        k_gn_bwd_reduce_arg<<<dim3((unsigned)wr, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(p);
+        int rc = check_launch("gn_bwd_reduce_arg");
+        if (rc) return rc;
+        k_gn_bwd_apply_arg<<<dim3((unsigned)wa, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(p);
+        return check_launch("gn_bwd_apply_arg");
+    }
+    const int rpp = 256 / C;
+    long long workers = (rows + rpp - 1) / rpp, wr = (rows + rpp * 16 - 1) / (rpp * 16);   // >= 16 rows per reducing thread
     if (workers > cap) workers = cap;
+    if (wr > cap) wr = cap;
     dim3 grid((unsigned)workers, (unsigned)B);
-    k_gn_bwd_reduce<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    k_gn_bwd_reduce<<<dim3((unsigned)wr, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(p);
     int rc = check_launch("gn_bwd_reduce");
     if (rc) return rc;
     k_gn_bwd_apply<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     return check_launch("gn_bwd_apply");
+}
+
+extern "C" int pvraft_gn_act_maxk_fwd(const float* x, const double* stats, const float* gamma, const float* beta, double count, int act,
+                                      float slope, int B, int64_t pts_per_sample, int C, float* y, uint8_t* arg, const float* slope_dev,
+                                      void* stream) {
+    if (!x || !stats || !gamma || !beta || !y || !arg || B <= 0 || pts_per_sample <= 0) return fail(PVRAFT_ERR_BAD_ARG, "gn_act_maxk: bad argument");
+    if (C > 256 || C % PVRAFT_GN_GROUPS) return fail(PVRAFT_ERR_UNSUPPORTED, "gn_act_maxk: C=%d", C);
+    const long long total = (long long)B * pts_per_sample * C;
+    k_gn_act_maxk<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, stats, gamma, beta, count, act, slope, B,
+                                                                                      (long long)pts_per_sample, C, y, arg, slope_dev);
+    return check_launch("gn_act_maxk");
 }
 
 extern "C" int pvraft_edge_fwd(const float* P, const int32_t* nbr, float* E, int B, int N, int C, double* stats, void* stream) {

@@ -360,7 +360,26 @@ def linear_wgrad(x, dy, dw, db=None):
            'linear_wgrad')
 
 
-def gn_act_bwd(x, dy, stats, gamma, beta, count, act, slope, want_dslope=False, slope_dev=None):
+def linear_bwd_small(x, dy, w, dw, db=None, want_dx=False):
+    """cin <= 4, cout in {32,64,128}: dw += dy^T x, db += column sums, and dx = dy w (returned, or None) in one pass over dy."""
+    rows = x.shape[0] * x.shape[1]
+    dx = torch.empty_like(x) if want_dx else None
+    _count(lib().pvraft_linear_bwd_small(_p(x), _p(dy), _p(w), rows, x.shape[-1], dy.shape[-1], w.shape[-1], _p(dw), dw.shape[-1], _p(db),
+                                         _p(dx), _stream()), 'linear_bwd_small')
+    return dx
+
+
+def gn_act_maxk(x, stats, gamma, beta, count, act, slope, slope_dev=None):
+    """x [B, pts*32, C] -> (max over each point's 32 rows of act(GN(x)) [B,pts,C], arg uint8 [B,pts,C]), one pass."""
+    b, rows, c = x.shape
+    y = torch.empty(b, rows // 32, c, dtype=torch.float32, device=x.device)
+    arg = torch.empty(b, rows // 32, c, dtype=torch.uint8, device=x.device)
+    _count(lib().pvraft_gn_act_maxk_fwd(_p(x), _p(stats, torch.float64), _p(gamma), _p(beta), float(count), act, float(slope), b,
+                                        rows // 32, c, _p(y), _p(arg, torch.uint8), _p(slope_dev), _stream()), 'gn_act_maxk')
+    return y, arg
+
+
+def gn_act_bwd(x, dy, stats, gamma, beta, count, act, slope, want_dslope=False, slope_dev=None, arg=None):
     """-> (dx, dgamma [C] f32, dbeta [C] f32, dslope [1] f32 or None)."""
     b, rows, c = x.shape
     dev = x.device
@@ -369,7 +388,7 @@ def gn_act_bwd(x, dy, stats, gamma, beta, count, act, slope, want_dslope=False, 
     dx = torch.empty_like(x)
     _count(lib().pvraft_gn_act_bwd(_p(x), _p(dy), _p(stats, torch.float64), _p(gamma), _p(beta), float(count), act, float(slope), b, rows,
                                    c, gsum.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), dslope.data_ptr() if want_dslope else None,
-                                   _p(dx), _p(slope_dev), _stream()), 'gn_act_bwd')
+                                   _p(dx), _p(slope_dev), _p(arg, torch.uint8), _stream()), 'gn_act_bwd')
     return dx, dgamma.float(), dbeta.float(), (dslope.float() if want_dslope else None)
 
 

@@ -7,6 +7,7 @@ The forward runs layer by layer -- the fused inference kernels keep no activatio
 
     LinearFn        1x1 convolution           pvraft_linear_fwd (y, and dx = dy.W through the transposed weight) + pvraft_linear_wgrad
     GnActFn         GroupNorm(8) + act        pvraft_gn_act_fwd / pvraft_gn_act_bwd
+    GnActMaxFn      ... + max over 32 rows    pvraft_gn_act_maxk_fwd / pvraft_gn_act_bwd (arg form: no dense max gradient)
     EdgeFn          SetConv edge stage        pvraft_edge_fwd / pvraft_edge_bwd          (model/flot/gconv.py:65-73)
     MaxKFn          max over 32 neighbours    pvraft_maxk_fwd / pvraft_maxk_bwd          (gconv.py:80, model/corr.py:92)
     CorrInitFn      truncated correlation     tcgen05 GEMM + top-k + reorder / pvraft_corr_init_bwd (sparse)   (corr.py:31-42,95-100)
@@ -51,6 +52,12 @@ class LinearFn(torch.autograd.Function):
         x, w2 = ctx.saved_tensors
         dy = dy.contiguous()
         dx = None
+        if w2.shape[1] <= 4 and w2.shape[0] in (32, 64, 128):
+            # the edge-level layers (rows = B*N*32, three or four input columns): one pass over dy for all three gradients
+            dw = torch.zeros_like(w2)
+            db = torch.zeros(w2.shape[0], dtype=torch.float32, device=w2.device) if ctx.has_bias else None
+            dx = ops.linear_bwd_small(x, dy, w2, dw, db, want_dx=ctx.needs_input_grad[0])
+            return dx, dw.reshape(ctx.w_shape), db, None
         if ctx.needs_input_grad[0]:
             # dx = dy . W: the same kernel with the transposed weight, 128 output columns (the kernel's limit) at a time
             cin = w2.shape[1]
@@ -97,6 +104,36 @@ def gn_act(x, stats, gn, act=ACT_LRELU, slope=0.1, prelu=None):
     """prelu: an nn.PReLU whose one-element weight is the slope -- handed to the kernels as a device pointer (the optimizer
     changes it every step; a host read-back would synchronise the stream twice per RAFT iteration)."""
     return GnActFn.apply(x, stats, gn.weight, gn.bias, None if prelu is None else prelu.weight, act, slope)
+
+
+class GnActMaxFn(torch.autograd.Function):
+    """max over each point's 32 consecutive rows of act(GroupNorm8(x)): [B,N*32,C] -> [B,N,C] (gconv.py:76-80, corr.py:87-92).
+    One forward pass over x; in the backward the dense gradient of the max (31/32 zeros) is never materialised: the GroupNorm
+    backward reads d(max) [B,N,C] and the arg-max directly."""
+
+    @staticmethod
+    def forward(ctx, x, stats, gamma, beta, slope_param, act, slope):
+        b, rows, c = x.shape
+        count = float(rows) * (c // 8)
+        x = x.contiguous()
+        sdev = None if slope_param is None else slope_param.detach().reshape(-1).contiguous()
+        y, arg = ops.gn_act_maxk(x, stats, gamma.detach(), beta.detach(), count, act, slope, slope_dev=sdev)
+        ctx.save_for_backward(x, stats, gamma.detach(), beta.detach(), arg, *(() if sdev is None else (sdev,)))
+        ctx.cfg = (count, act, float(slope), slope_param is not None, None if slope_param is None else slope_param.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats, gamma, beta, arg = ctx.saved_tensors[:5]
+        count, act, slope, has_slope, slope_shape = ctx.cfg
+        sdev = ctx.saved_tensors[5] if has_slope else None
+        dx, dgamma, dbeta, dslope = ops.gn_act_bwd(x, dy.contiguous(), stats, gamma, beta, count, act, slope, has_slope, slope_dev=sdev,
+                                                   arg=arg)
+        return dx, None, dgamma, dbeta, (dslope.reshape(slope_shape) if has_slope else None), None, None
+
+
+def gn_act_max(x, stats, gn, act=ACT_LRELU, slope=0.1, prelu=None):
+    return GnActMaxFn.apply(x, stats, gn.weight, gn.bias, None if prelu is None else prelu.weight, act, slope)
 
 
 class EdgeFn(torch.autograd.Function):
@@ -192,8 +229,7 @@ def set_conv(m, x, graph):
     p = linear(x, w[:, :cin])
     e = linear(graph._rel.reshape(b, n * 32, 3), w[:, cin:])
     t, st = EdgeFn.apply(p, e, graph.nbr)
-    y = gn_act(t, st, m.gn1)
-    z2, st2 = linear(MaxKFn.apply(y), m.fc2.weight, None, True)
+    z2, st2 = linear(gn_act_max(t, st, m.gn1), m.fc2.weight, None, True)
     z3, st3 = linear(gn_act(z2, st2, m.gn2), m.fc3.weight, None, True)
     return gn_act(z3, st3, m.gn3)
 
@@ -211,7 +247,7 @@ def corr_features(cb, vox, sel):
     y1, st1 = linear(vox, oc[0].weight, oc[0].bias, True)
     vfeat = linear(gn_act(y1, st1, oc[1], prelu=oc[2]), oc[3].weight, oc[3].bias)
     k1, stk = linear(sel, kc[0].weight, kc[0].bias, True)
-    kfeat = linear(MaxKFn.apply(gn_act(k1, stk, kc[1], prelu=kc[2])), cb.knn_out.weight, cb.knn_out.bias)
+    kfeat = linear(gn_act_max(k1, stk, kc[1], prelu=kc[2]), cb.knn_out.weight, cb.knn_out.bias)
     return vfeat + kfeat
 
 

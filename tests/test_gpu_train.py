@@ -44,7 +44,8 @@ def leaf(t, dev=None):
 # single Functions
 # ----------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('b,r,cin,cout,bias', [(2, 300, 64, 64, True), (1, 1000, 81, 128, True), (2, 257, 3, 16, False),
-                                               (1, 4096, 192, 128, True), (2, 130, 128, 3, True), (1, 70, 4, 64, True)])
+                                               (1, 4096, 192, 128, True), (2, 130, 128, 3, True), (1, 70, 4, 64, True),
+                                               (2, 4099, 3, 32, False), (1, 9000, 3, 128, True), (2, 2500, 4, 64, True), (1, 33, 2, 64, False)])
 def test_linear_fn(dev, b, r, cin, cout, bias):
     from pvraft_b200 import train as T
     g = torch.Generator().manual_seed(cin * 131 + cout)
@@ -91,6 +92,38 @@ def test_gn_act_fn(dev, b, r, c, act):
     code = ops.ACT_NONE if act == 'none' else ops.ACT_LRELU
     y = T.GnActFn.apply(xd, stats, gd, bd, sd if act == 'prelu' else None, code, 0.25 if act == 'prelu' else 0.1)
     y.backward(gy.to(dev))
+    assert rel_err(y.detach().cpu(), yr.detach()) < 1e-5
+    assert rel_err(xd.grad.cpu(), xr.grad) < 5e-5
+    assert rel_err(gd.grad.cpu(), gr.grad) < 5e-5 and rel_err(bd.grad.cpu(), br.grad) < 5e-5
+    if act == 'prelu':
+        assert rel_err(sd.grad.cpu(), sr.grad) < 5e-5
+
+
+@pytest.mark.parametrize('b,pts,c,act', [(2, 64, 64, 'lrelu'), (1, 301, 16, 'lrelu'), (2, 40, 128, 'prelu'), (1, 17, 96, 'none')])
+def test_gn_act_max_fn(dev, b, pts, c, act):
+    """GroupNorm + activation + max over 32 rows as one Function: values, arg-max routing and every gradient against autograd
+    of the unfused float64 chain (the backward never builds the dense gradient of the max)."""
+    from pvraft_b200 import ops, train as T
+    r = pts * 32
+    g = torch.Generator().manual_seed(c + pts)
+    x = torch.randn(b, r, c, generator=g) * 1.7 + 0.4
+    gamma, beta = torch.randn(c, generator=g), torch.randn(c, generator=g) * 0.2
+    slope = torch.tensor([0.25])
+    gy = torch.randn(b, pts, c, generator=g)
+    xr, gr, br, sr = leaf(x).double(), leaf(gamma).double(), leaf(beta).double(), leaf(slope).double()
+    for t in (xr, gr, br, sr):
+        t.retain_grad()
+    n = F.group_norm(xr.transpose(1, 2), 8, gr, br, 1e-5).transpose(1, 2)
+    a = {'lrelu': lambda t: F.leaky_relu(t, 0.1), 'prelu': lambda t: torch.where(t >= 0, t, sr * t), 'none': lambda t: t}[act](n)
+    yr = a.view(b, pts, 32, c).max(2).values
+    yr.backward(gy.double())
+    xd, gd, bd, sd = leaf(x, dev), leaf(gamma, dev), leaf(beta, dev), leaf(slope, dev)
+    xs = xd.detach().double().reshape(b, r, 8, c // 8)
+    stats = torch.stack([xs.sum((1, 3)), (xs ** 2).sum((1, 3))], -1).contiguous()
+    code = ops.ACT_NONE if act == 'none' else ops.ACT_LRELU
+    y = T.GnActMaxFn.apply(xd, stats, gd, bd, sd if act == 'prelu' else None, code, 0.25 if act == 'prelu' else 0.1)
+    y.backward(gy.to(dev))
+    assert y.shape == (b, pts, c)
     assert rel_err(y.detach().cpu(), yr.detach()) < 1e-5
     assert rel_err(xd.grad.cpu(), xr.grad) < 5e-5
     assert rel_err(gd.grad.cpu(), gr.grad) < 5e-5 and rel_err(bd.grad.cpu(), br.grad) < 5e-5
