@@ -397,7 +397,7 @@ PVRAFT_API int pvraft_linear_wgrad(const float* x, const float* dy, int64_t rows
 PVRAFT_API int pvraft_gn_act_bwd(const float* x, const float* dy, const double* stats, const float* gamma, const float* beta, double count,
                       int act, float slope, int B, int64_t rows, int C, double* gsum, double* dgamma, double* dbeta, double* dslope,
                       float* dx, const float* slope_dev, const uint8_t* arg, void* stream);
-/* Backward of a linear layer with cin <= 4 and cout in {32,64,128} (the SetConv edge term and the knn_conv: rows = B*N*32) in one
+/* Backward of a linear layer with cin <= 4 and cout in {16,32,48,64,96,128} (the SetConv edge term and the knn_conv: rows = B*N*32) in one
  * pass over dy: dW [cout,dw_ld] += dy^T x, db [cout] += column sums (or NULL), dx [rows,cin] = dy W (or NULL).  W is [cout,w_ld]. */
 PVRAFT_API int pvraft_linear_bwd_small(const float* x, const float* dy, const float* W, int64_t rows, int cin, int cout, int w_ld, float* dW,
                             int dw_ld, float* db, float* dx, void* stream);

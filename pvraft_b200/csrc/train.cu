@@ -105,10 +105,11 @@ template <int LPR>
 __global__ void __launch_bounds__(256) k_linear_bwd_small(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ W,
                                                           long long rows, int cin, int w_ld, float* __restrict__ dW, int dw_ld,
                                                           float* __restrict__ db, float* __restrict__ dx) {
-    constexpr int COUT = 16 * LPR, RPW = 32 / LPR;
+    constexpr int COUT = 16 * LPR, RPW = 32 / LPR;   // LPR = 3 or 6 leaves two lanes of the warp idle
     __shared__ float4 s_w[COUT];
     __shared__ float s_acc[COUT][5];
     const int lane = lane_id(), w = warp_id(), q = lane % LPR, rr = lane / LPR;
+    const bool active = rr < RPW;
     for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         for (int k = 0; k < cin; ++k) v[k] = __ldg(W + (size_t)i * w_ld + k);
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(256) k_linear_bwd_small(const float* __restric
     float4 d4[4];
     float xv[4];
     auto fetch = [&](long long row) {
-        if (row < rows) {
+        if (active && row < rows) {
             const float4* dp = reinterpret_cast<const float4*>(dy + (size_t)row * COUT + q * 16);
 #pragma unroll
             for (int k = 0; k < 4; ++k) d4[k] = __ldg(dp + k);
@@ -161,30 +162,26 @@ __global__ void __launch_bounds__(256) k_linear_bwd_small(const float* __restric
             }
         }
         if (dx) {
+            float tot[4] = {0.f, 0.f, 0.f, 0.f};
+            const int row_lane0 = (active ? rr : 0) * LPR;
 #pragma unroll
-            for (int m = 1; m < LPR; m <<= 1) {
+            for (int m = 0; m < LPR; ++m) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) sx[k] += __shfl_xor_sync(0xffffffffu, sx[k], m);
+                for (int k = 0; k < 4; ++k) tot[k] += __shfl_sync(0xffffffffu, sx[k], row_lane0 + m);
             }
-            if (q == 0 && r < rows) {
+            if (active && q == 0 && r < rows) {
                 if (cin == 4) {
-                    *reinterpret_cast<float4*>(dx + (size_t)r * 4) = make_float4(sx[0], sx[1], sx[2], sx[3]);
+                    *reinterpret_cast<float4*>(dx + (size_t)r * 4) = make_float4(tot[0], tot[1], tot[2], tot[3]);
                 } else {
-                    for (int k = 0; k < cin; ++k) dx[(size_t)r * cin + k] = sx[k];
+                    for (int k = 0; k < cin; ++k) dx[(size_t)r * cin + k] = tot[k];
                 }
             }
         }
     }
-    // rows of the warp -> lanes rr == 0, then the CTA's 8 warps -> shared -> one global atomic per entry
+    // the lanes' partial sums -> shared -> one global atomic per entry and CTA (once per CTA lifetime)
+    if (active) {
 #pragma unroll
-    for (int o = 0; o < 16; ++o) {
-#pragma unroll
-        for (int m = LPR; m < 32; m <<= 1) {
-            accb[o] += __shfl_xor_sync(0xffffffffu, accb[o], m);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc[o][k] += __shfl_xor_sync(0xffffffffu, acc[o][k], m);
-        }
-        if (rr == 0) {
+        for (int o = 0; o < 16; ++o) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) atomicAdd(&s_acc[q * 16 + o][k], acc[o][k]);
             atomicAdd(&s_acc[q * 16 + o][4], accb[o]);
@@ -686,19 +683,27 @@ extern "C" int pvraft_linear_wgrad(const float* x, const float* dy, int64_t rows
 extern "C" int pvraft_linear_bwd_small(const float* x, const float* dy, const float* W, int64_t rows, int cin, int cout, int w_ld, float* dW,
                                        int dw_ld, float* db, float* dx, void* stream) {
     if (!x || !dy || !W || !dW || rows <= 0) return fail(PVRAFT_ERR_BAD_ARG, "linear_bwd_small: bad argument");
-    if (cin < 1 || cin > 4 || (cout != 32 && cout != 64 && cout != 128))
-        return fail(PVRAFT_ERR_UNSUPPORTED, "linear_bwd_small: cin=%d cout=%d (cin <= 4, cout in {32,64,128})", cin, cout);
+    const int lpr = cout / 16;
+    if (cin < 1 || cin > 4 || cout % 16 || !(lpr == 1 || lpr == 2 || lpr == 3 || lpr == 4 || lpr == 6 || lpr == 8))
+        return fail(PVRAFT_ERR_UNSUPPORTED, "linear_bwd_small: cin=%d cout=%d (cin <= 4, cout in {16,32,48,64,96,128})", cin, cout);
     if ((reinterpret_cast<uintptr_t>(dy) & 15) || (cin == 4 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx)) & 15)))
         return fail(PVRAFT_ERR_BAD_ARG, "linear_bwd_small: dy (and x, dx when cin == 4) must be 16-byte aligned");
-    const int lpr = cout / 16, rpc = 8 * (32 / lpr);
+    const int rpc = 8 * (32 / lpr);
     long long ctas = (rows + rpc - 1) / rpc;
     const long long cap = (long long)sm_count();   // 152 registers x 256 threads: one resident CTA per SM
     if (ctas > cap) ctas = cap;
     const int wl = w_ld > 0 ? w_ld : cin, dl = dw_ld > 0 ? dw_ld : cin;
     cudaStream_t st = (cudaStream_t)stream;
-    if (lpr == 2) k_linear_bwd_small<2><<<(unsigned)ctas, 256, 0, st>>>(x, dy, W, rows, cin, wl, dW, dl, db, dx);
-    else if (lpr == 4) k_linear_bwd_small<4><<<(unsigned)ctas, 256, 0, st>>>(x, dy, W, rows, cin, wl, dW, dl, db, dx);
-    else k_linear_bwd_small<8><<<(unsigned)ctas, 256, 0, st>>>(x, dy, W, rows, cin, wl, dW, dl, db, dx);
+#define PVRAFT_LBS(L) k_linear_bwd_small<L><<<(unsigned)ctas, 256, 0, st>>>(x, dy, W, rows, cin, wl, dW, dl, db, dx)
+    switch (lpr) {
+        case 1: PVRAFT_LBS(1); break;
+        case 2: PVRAFT_LBS(2); break;
+        case 3: PVRAFT_LBS(3); break;
+        case 4: PVRAFT_LBS(4); break;
+        case 6: PVRAFT_LBS(6); break;
+        default: PVRAFT_LBS(8); break;
+    }
+#undef PVRAFT_LBS
     return check_launch("linear_bwd_small");
 }
 

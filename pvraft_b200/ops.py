@@ -361,7 +361,7 @@ def linear_wgrad(x, dy, dw, db=None):
 
 
 def linear_bwd_small(x, dy, w, dw, db=None, want_dx=False):
-    """cin <= 4, cout in {32,64,128}: dw += dy^T x, db += column sums, and dx = dy w (returned, or None) in one pass over dy."""
+    """cin <= 4, cout in {16,32,48,64,96,128}: dw += dy^T x, db += column sums, and dx = dy w (returned, or None) in one pass over dy."""
     rows = x.shape[0] * x.shape[1]
     dx = torch.empty_like(x) if want_dx else None
     _count(lib().pvraft_linear_bwd_small(_p(x), _p(dy), _p(w), rows, x.shape[-1], dy.shape[-1], w.shape[-1], _p(dw), dw.shape[-1], _p(db),

@@ -52,7 +52,7 @@ class LinearFn(torch.autograd.Function):
         x, w2 = ctx.saved_tensors
         dy = dy.contiguous()
         dx = None
-        if w2.shape[1] <= 4 and w2.shape[0] in (32, 64, 128):
+        if w2.shape[1] <= 4 and w2.shape[0] in (16, 32, 48, 64, 96, 128):
             # the edge-level layers (rows = B*N*32, three or four input columns): one pass over dy for all three gradients
             dw = torch.zeros_like(w2)
             db = torch.zeros(w2.shape[0], dtype=torch.float32, device=w2.device) if ctx.has_bias else None

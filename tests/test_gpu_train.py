@@ -45,7 +45,8 @@ def leaf(t, dev=None):
 # ----------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('b,r,cin,cout,bias', [(2, 300, 64, 64, True), (1, 1000, 81, 128, True), (2, 257, 3, 16, False),
                                                (1, 4096, 192, 128, True), (2, 130, 128, 3, True), (1, 70, 4, 64, True),
-                                               (2, 4099, 3, 32, False), (1, 9000, 3, 128, True), (2, 2500, 4, 64, True), (1, 33, 2, 64, False)])
+                                               (2, 4099, 3, 32, False), (1, 9000, 3, 128, True), (2, 2500, 4, 64, True), (1, 33, 2, 64, False),
+                                               (1, 5000, 3, 16, False), (2, 3001, 3, 48, True), (1, 2777, 4, 96, True)])
 def test_linear_fn(dev, b, r, cin, cout, bias):
     from pvraft_b200 import train as T
     g = torch.Generator().manual_seed(cin * 131 + cout)
