@@ -178,10 +178,22 @@ __global__ void __launch_bounds__(256) k_linear_bwd_small(const float* __restric
             }
         }
     }
-    // the lanes' partial sums -> shared -> one global atomic per entry and CTA (once per CTA lifetime)
-    if (active) {
+    // rows of the warp -> its first row's lanes (a shuffle tree over the row index; idle lanes hold zeros), then the CTA's
+    // 8 warps -> shared -> one global atomic per entry and CTA
 #pragma unroll
-        for (int o = 0; o < 16; ++o) {
+    for (int o = 0; o < 16; ++o) {
+#pragma unroll
+        for (int m = 1; m < RPW; m <<= 1) {
+            const bool take = lane + m * LPR < 32;
+            const float t = __shfl_down_sync(0xffffffffu, accb[o], m * LPR);
+            accb[o] += take ? t : 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float u = __shfl_down_sync(0xffffffffu, acc[o][k], m * LPR);
+                acc[o][k] += take ? u : 0.f;
+            }
+        }
+        if (rr == 0) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) atomicAdd(&s_acc[q * 16 + o][k], acc[o][k]);
             atomicAdd(&s_acc[q * 16 + o][4], accb[o]);
