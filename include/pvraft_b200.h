@@ -218,6 +218,9 @@ typedef struct pvraft_tc_linear_args {
     float* flow_user;       /* FLOW: second copy of the flow, row r written at row row_map[r] ([B*N,3]) -- the caller's
                                point order when the cloud was spatially reordered for locality -- or NULL */
     const int32_t* row_map; /* FLOW: [B*N] destination rows of flow_user */
+    int params_settled;     /* nonzero: w_hi, w_lo, bias, bias2, w3, b3 were last written at least three launches ago on this
+                               stream (or before a synchronisation).  The kernel is launched with programmatic stream
+                               serialization and then fetches them while the previous kernel drains.  0 is always safe. */
 } pvraft_tc_linear_args;
 
 PVRAFT_API int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream);

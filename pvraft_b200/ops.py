@@ -5,6 +5,7 @@ hot path happens inside libpvraft_b200.so.  All wrappers require contiguous CUDA
 on anything else -- there is deliberately no CPU / eager fallback.
 """
 import ctypes as C
+import os
 import threading
 import weakref
 
@@ -170,6 +171,7 @@ def linear(x, weight, bias=None, *, cin=None, w_ld=0, w_cin=0, in_mode=IN_PLAIN,
 
 
 _TC_WEIGHTS = {}
+_EARLY_PARAMS = os.environ.get('PVRAFT_TC_EARLY_PARAMS', '1') != '0'
 TC_PLAIN, TC_GRU_ZR, TC_GRU_Q, TC_FLOW = 0, 1, 2, 3
 
 
@@ -186,6 +188,7 @@ def tc_weights(weights, col0=0, cols=None, k_pad=None, kcat=False):
         refs, versions, ptrs, result = hit
         if all(r() is w and w._version == v and w.data_ptr() == p for r, w, v, p in zip(refs, weights, versions, ptrs)):
             return result
+    _TLS.unsettled = 3   # the split below writes what the next tensor-core launches read: see tc_linear()
     mats = [w.detach().reshape(w.shape[0], -1) for w in weights]
     if kcat:   # [W_a | W_b | ...] along K: one GEMM over concatenated sources adds the layers' outputs
         mats = [torch.cat(mats, 1).contiguous()]
@@ -221,6 +224,7 @@ def derived(tensors, tag, fn):
         refs, versions, ptrs, value = hit
         if all(r() is t and t._version == v and t.data_ptr() == p for r, t, v, p in zip(refs, tensors, versions, ptrs)):
             return value
+    _TLS.unsettled = 3   # fn may launch kernels that write a folded weight / bias
     value = fn(*tensors)
     if len(_DERIVED) > 512:
         _DERIVED.clear()
@@ -290,6 +294,12 @@ def tc_linear(sources, w, bias=None, *, in_min=None, in_stats=None, in_gamma=Non
     a.w3, a.b3, a.coords1, a.coords2 = _p(w3), _p(b3), _p(coords1), _p(coords2)
     a.coords2_out, a.flow_out = _p(coords2_out), _p(flow_out)
     a.flow_user, a.row_map = _p(flow_user), _p(row_map, torch.int32)
+    # The kernel may fetch its parameters while the previous kernel drains (PDL) once they are settled: not during the
+    # three tensor-core launches that follow a weight split or a re-derived folded parameter on this thread.
+    pending = getattr(_TLS, 'unsettled', 0)
+    a.params_settled = 1 if pending == 0 and _EARLY_PARAMS else 0
+    if pending:
+        _TLS.unsettled = pending - 1
     _count(lib().pvraft_tc_linear_fwd(C.byref(a), _stream()), 'tc_linear')
     return out
 
