@@ -71,6 +71,10 @@ struct TcParams {
     int stages;               // depth of the shared-memory ring (1..4)
     int w_resident;           // 1: all weight boxes are loaded once per CTA and stay in shared memory
     int settled;              // 1: weights / biases may be read before griddepcontrol.wait
+    int* done;                // [B] or null: every epilogue warp adds 1 per finished tile of the sample (release)
+    const int* wait_on;       // [B] or null: the `done` counters of the previous launch, which produced this layer's inputs.
+                              // Non-null: the grid-wide dependency wait is replaced by per-sample waits in the TMA producer
+    unsigned wait_target;     // 8 * tiles per sample
     int dbg;                  // 1: CTA 0 records a globaltimer timeline into g_tc_clock
     int gn_kb;                // k-blocks (from the start: source 0) that go through the GroupNorm prologue
     int out_ld;               // row stride of `out` in floats (cout, or cout + 3 with a tail)
@@ -167,11 +171,17 @@ __device__ __forceinline__ void stage_store16(float* __restrict__ stg, int lane,
 }
 // the inverse: a [32 rows x 16 columns] block of a row-major global tensor, loaded as 8 rows x 64 B per instruction and handed
 // to the thread that owns each row (thread-per-row loads would touch 32 sectors per instruction)
-__device__ __forceinline__ void stage_load16(float* __restrict__ stg, int lane, const float* __restrict__ gbase, int ld, float (&x)[16]) {
+// COHERENT: the operand may have been written by the previous launch while this one was already running (chained launches):
+// ld.global.cg (L2) instead of the non-coherent path.
+template <bool COHERENT = false>
+__device__ __forceinline__ void stage_load16(float* __restrict__ stg, int lane, const float* gbase, int ld, float (&x)[16]) {
     const int rsub = lane >> 2, cq = lane & 3;
     float4 o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = __ldg(reinterpret_cast<const float4*>(gbase + (size_t)(j * 8 + rsub) * ld + cq * 4));
+    for (int j = 0; j < 4; ++j) {
+        const float4* src = reinterpret_cast<const float4*>(gbase + (size_t)(j * 8 + rsub) * ld + cq * 4);
+        o[j] = COHERENT ? __ldcg(src) : __ldg(src);
+    }
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(stg + (j * 8 + rsub) * kTcPitch16 + cq * 4) = o[j];
@@ -181,6 +191,14 @@ __device__ __forceinline__ void stage_load16(float* __restrict__ stg, int lane, 
         const float4 v = *reinterpret_cast<const float4*>(stg + lane * kTcPitch16 + q * 4);
         x[q * 4 + 0] = v.x; x[q * 4 + 1] = v.y; x[q * 4 + 2] = v.z; x[q * 4 + 3] = v.w;
     }
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const int* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu(int* p) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
 __device__ __forceinline__ bool telect_one() {
     unsigned pred;
@@ -366,7 +384,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, unsigned tacc, in
             tmem_ld16(tl + (unsigned)c, vq);
             float o[16], hh[16], zz[16];
             stage_load16(stg, lane, p.h + (size_t)(row0 + quad * 32) * 64 + c, 64, hh);
-            stage_load16(stg, lane, p.z + (size_t)(row0 + quad * 32) * 64 + c, 64, zz);
+            stage_load16<true>(stg, lane, p.z + (size_t)(row0 + quad * 32) * 64 + c, 64, zz);   // z comes from the launch before
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 hv = make_float4(hh[q * 4], hh[q * 4 + 1], hh[q * 4 + 2], hh[q * 4 + 3]);
@@ -477,7 +495,11 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
         if (warp == 0 && lane == 0 && p.w_resident) load_weights();
         if (warp >= 10) load_bias();
     }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // Chained on the previous launch (p.wait_on): no grid-wide wait -- the TMA producer waits per sample on that launch's
+    // `done` counters instead, so this CTA starts on the tiles whose inputs are complete while the stragglers of the
+    // previous launch still run on other SMs.  Everything else this kernel reads is older than the previous launch,
+    // which itself only signals after its own dependencies resolved.
+    if (p.wait_on == nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (!p.settled && warp >= 10) load_bias();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -490,9 +512,18 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
             if (p.w_resident && !p.settled) load_weights();
             const unsigned tx = (unsigned)(kTcABytes * (p.minmax ? 2 : 1) + (p.w_resident ? 0 : 2 * w_bytes));
             TcCursor cw;
+            int ready_sample = -1;
             for (int step = 0; step < total_steps; ++step, cw.next(num_kb, S)) {
                 const int s = cw.s, kb = cw.kb;
                 const int row0 = (blockIdx.x + cw.ti * gridDim.x) * kTcM;
+                if (p.wait_on != nullptr && kb == 0) {
+                    const int sample = row0 / p.pts_per_sample;
+                    if (sample != ready_sample) {   // all tiles of this sample (rows and GroupNorm sums) are out
+                        while (ld_acquire_gpu(p.wait_on + sample) < p.wait_target) __nanosleep(40);
+                        asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire -> the TMA reads below
+                        ready_sample = sample;
+                    }
+                }
                 tmbar_wait(&s_empty[s], cw.phase ^ 1u);   // the MMAs that read this stage last time have retired
                 unsigned char* st = tiles + (size_t)s * stage_bytes;
                 tmbar_expect_tx(&s_full[s], tx);
@@ -564,7 +595,7 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
         if (grp == 1) cp.next(num_kb, S);
         for (int step = grp; step < total_steps; step += 2) {
             const int kb = cp.kb, s = cp.s;
-            if (p.in_stats != nullptr) {
+            auto gn_table = [&]() {
                 const int tile = blockIdx.x + cp.ti * gridDim.x;
                 if (tile < table_first || tile >= table_end) {   // folded GroupNorm affine of every input channel of this sample
                     const int sample = tile / tiles_per_sample;
@@ -573,14 +604,20 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // the group is done with the previous table
                     const int gn_k = p.gn_kb * kTcKB, gsz = gn_k / PVRAFT_GN_GROUPS;
                     for (int k = t; k < gn_k; k += 128) {
-                        const GnAffine af = gn_affine(p.in_stats + (size_t)sample * 16 + (k / gsz) * 2, p.in_count, __ldg(p.in_gamma + k), __ldg(p.in_beta + k));
+                        const double* sp = p.in_stats + (size_t)sample * 16 + (k / gsz) * 2;
+                        const double st[2] = {__ldcg(sp), __ldcg(sp + 1)};   // (written by the launch before: L2, not the nc path)
+                        const GnAffine af = gn_affine(st, p.in_count, __ldg(p.in_gamma + k), __ldg(p.in_beta + k));
                         g_scale[k] = af.scale;
                         g_shift[k] = af.shift;
                     }
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
                 }
-            }
+            };
+            // the sums are complete once the previous launch is: before the box wait normally (the table overlaps the TMA
+            // latency), after it when chained (the producer issued this box only after the sample's `done` count was reached)
+            if (p.in_stats != nullptr && p.wait_on == nullptr) gn_table();
             tmbar_wait(&s_full[s], cp.phase);   // the raw box(es) of this k-block have landed
+            if (p.in_stats != nullptr && p.wait_on != nullptr) gn_table();
             unsigned char* st = tiles + (size_t)s * stage_bytes;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -626,10 +663,14 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
             tmbar_wait(&s_acc_full[acc], acc_phase);
             TC_MARK(threadIdx.x == 320 && ti < 4, 24 + ti);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            tc_epilogue(p, tmem + (unsigned)acc * acc_cols, quad, half, lane, row0, row0 / p.pts_per_sample, s_bias, s_estage, s_part);
+            const int sample = row0 / p.pts_per_sample;
+            tc_epilogue(p, tmem + (unsigned)acc * acc_cols, quad, half, lane, row0, sample, s_bias, s_estage, s_part);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) tmbar_arrive(&s_acc_empty[acc]);   // one arrival per epilogue warp
+            if (lane == 0) {
+                tmbar_arrive(&s_acc_empty[acc]);   // one arrival per epilogue warp
+                if (p.done != nullptr) red_release_gpu(p.done + sample);   // this warp's rows (and sums) of the tile are out
+            }
             TC_MARK(threadIdx.x == 320 && ti < 4, 28 + ti);
         }
     }
@@ -739,6 +780,8 @@ extern "C" int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream
     p.w3 = a->w3; p.b3 = a->b3; p.coords1 = a->coords1; p.coords2 = a->coords2; p.coords2_out = a->coords2_out; p.flow_out = a->flow_out; p.flow_user = a->flow_user; p.row_map = a->row_map;
     p.out_ld = a->tail ? a->cout + 3 : a->cout;
     p.settled = a->params_settled ? 1 : 0;
+    p.done = a->done;
+    p.wait_target = 8u * (unsigned)(a->N / kTcM);
     if ((rc = tc_make_map(&mw_hi, a->w_hi, a->n_pad, K, K, a->n_pad)) || (rc = tc_make_map(&mw_lo, a->w_lo, a->n_pad, K, K, a->n_pad))) return rc;
     CUtensorMap ma[3], mmin;
     for (int s = 0; s < 3; ++s) {   // unused slots repeat source 0 (a tensor map must be valid even if never dereferenced)
@@ -770,6 +813,8 @@ extern "C" int pvraft_tc_linear_fwd(const pvraft_tc_linear_args* a, void* stream
     const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());
     // launched with programmatic stream serialization: the kernel's prologue may start while the previous kernel drains
     static const bool pdl = []() { const char* e = getenv("PVRAFT_TC_PDL"); return !(e && atoi(e) == 0); }();
+    // chaining replaces the grid-wide wait, so it needs the early start PDL gives and parameters that are already in place
+    p.wait_on = (a->wait_on && pdl && p.settled) ? a->wait_on : nullptr;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kTcThreads);

@@ -142,7 +142,8 @@ class _RaftBase(nn.Module):
         use_tc = ops.tc_supported(n)
         # (hoisting the constant context part of the GRU pre-activations out of the loop -- K = 128 per iteration instead of 192 --
         #  was measured slower in round 1, 22.15 vs 21.72 ms per forward: the two extra per-point reads outweigh the shorter GEMM)
-        with ops.stats_arena(b, xyz1.device, 5 * num_iters):   # moments + 4 GroupNorm accumulators per iteration, one memset
+        # per iteration: moments + 4 GroupNorm accumulators + the completion counters of the 9 tensor-core launches; one memset
+        with ops.stats_arena(b, xyz1.device, 14 * num_iters):
             return self._iterate_body(xyz1, graph_context, net, inp, num_iters, keep_all, coords2, flow, preds, me, use_tc)
 
     def _iterate_body(self, xyz1, graph_context, net, inp, num_iters, keep_all, coords2, flow, preds, me, use_tc):
