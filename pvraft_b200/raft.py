@@ -35,8 +35,12 @@ def _records_grad(module):
 class _RaftBase(nn.Module):
     # CUDA-graph replay of the whole forward (encoders, correlation build, all iterations): the eager path costs ~28 us of
     # host time per launch (python + ctypes + tensor-map encodes), which bounds small batches (B <= 2: ~0.5 ms per
-    # iteration).  `use_cuda_graph = None` (default) replays graphs for inference batches of at most 2 samples, True / False
-    # (or PVRAFT_CUDA_GRAPH=1 / 0) force it on / off.  One graph per (B, N, num_iters); inputs are
+    # iteration) and leaves larger ones exposed to host jitter (at B = 8 the 431 launches of a forward have 45 us each: the
+    # same forward measured 19.5 ms on a quiet host and 20.5-21.3 ms next to a busy thread; replayed it is 19.5 ms either
+    # way).  `use_cuda_graph = None` (default) replays graphs for inference batches of at most 2 samples from the first call,
+    # and for larger batches from the SECOND call with the same shape and unchanged weights (a stream of differently sized
+    # clouds, or evaluation calls interleaved with optimizer steps, stays eager: a capture costs three forwards);
+    # True / False (or PVRAFT_CUDA_GRAPH=1 / 0) force it on / off.  One graph per (B, N, num_iters), at most 8 kept; inputs are
     # copied into the graph's static buffers, outputs are returned as copies.  The kernels read DERIVED copies of the weights
     # (tf32 hi/lo splits, folded products, bias sums, PReLU slopes known to the host) that are fixed at capture time, so a
     # graph is only valid for the parameter values it was captured with: every entry records (version, data_ptr) of all
@@ -49,6 +53,7 @@ class _RaftBase(nn.Module):
 
     def reset_graphs(self):
         self.__dict__.pop('_graphs', None)
+        self.__dict__.pop('_seen', None)
 
     def set_precision(self, mode):
         """'fp32' (default): the reference's arithmetic.  'bf16': the reduced-precision STATE mode of BASELINE.json configs[2] --
@@ -60,12 +65,18 @@ class _RaftBase(nn.Module):
         self.reset_graphs()
         return self
 
+    def _graph_key(self, xyz1, num_iters):
+        return (tuple(xyz1.shape), xyz1.device, int(num_iters), bool(self.sort_points))
+
+    def _stamp(self):
+        return tuple((q._version, q.data_ptr()) for q in self.parameters())
+
     def _graphed(self, p, num_iters):
         xyz1, xyz2 = p[0].detach().contiguous().float(), p[1].detach().contiguous().float()
         graphs = self.__dict__.setdefault('_graphs', {})
-        key = (tuple(xyz1.shape), xyz1.device, int(num_iters), bool(self.sort_points))
+        key = self._graph_key(xyz1, num_iters)
         entry = graphs.get(key)
-        stamp = tuple((q._version, q.data_ptr()) for q in self.parameters())
+        stamp = self._stamp()
         if entry is not None and entry[3] != stamp:
             entry = None                                   # weights changed since the capture: stale derived constants
         if entry is None:
@@ -82,6 +93,9 @@ class _RaftBase(nn.Module):
             l0 = ops.launch_count
             with torch.cuda.graph(graph):
                 static_out = self._forward_impl(static_in, num_iters)
+            graphs.pop(key, None)
+            while len(graphs) >= 8:                        # oldest capture out (its private memory pool goes with it)
+                graphs.pop(next(iter(graphs)))
             entry = graphs[key] = (graph, static_in, static_out, stamp, ops.launch_count - l0)
         graph, static_in, static_out, _, n_kernels = entry
         static_in[0].copy_(xyz1)
@@ -97,8 +111,18 @@ class _RaftBase(nn.Module):
             if _records_grad(self):
                 return self._forward_train(p, num_iters)
             graph = self.use_cuda_graph
-            if graph is None:    # automatic: small inference batches are host-bound (not inside an nn.DataParallel replica thread)
-                graph = p[0].shape[0] <= 2 and not getattr(self, '_is_replica', False)
+            if graph is None:    # automatic (never inside an nn.DataParallel replica thread)
+                if getattr(self, '_is_replica', False):
+                    graph = False
+                elif p[0].shape[0] <= 2:
+                    graph = True     # host-bound from the first call
+                else:                # larger batches: once the same shape has come back with the same weights
+                    seen = self.__dict__.setdefault('_seen', {})
+                    key, stamp = self._graph_key(p[0], num_iters), self._stamp()
+                    graph = seen.get(key) == stamp
+                    if len(seen) > 64:
+                        seen.clear()
+                    seen[key] = stamp
             if graph:
                 return self._graphed(p, num_iters)
             return self._forward_impl(p, num_iters)
