@@ -656,23 +656,29 @@ k_tc_linear(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant_
         // ===== epilogue: TMEM -> registers -> global, one accumulator buffer behind the MMA =====
         const int quad = warp & 3;          // a warp may only touch TMEM lanes 32*(warp%4) .. +31
         const int half = (warp - 10) >> 2;  // two warps per lane quadrant: 32-column chunks c0 = 32*half, +64, ...
+        // Completion signal of a tile (p.done: one release-add per epilogue warp and tile).  The release has to wait for the
+        // warp's outstanding stores, ~1 us if issued right behind them -- exposed, because this warp is alone on its
+        // scheduler.  So the signal of tile i is sent when the accumulator of tile i+1 arrives (its stores have long
+        // landed: the fence is free), and only the last tile signals at once.  A consumer loses nothing: it cannot run on
+        // this SM before this CTA exits, and samples that complete in an earlier round are not needed sooner.
+        int unsignalled = -1;
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int acc = ti & 1;
             const unsigned acc_phase = (unsigned)(ti >> 1) & 1u;
             const int row0 = (blockIdx.x + ti * gridDim.x) * kTcM;
             tmbar_wait(&s_acc_full[acc], acc_phase);
+            if (unsignalled >= 0 && lane == 0) red_release_gpu(p.done + unsignalled);
             TC_MARK(threadIdx.x == 320 && ti < 4, 24 + ti);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int sample = row0 / p.pts_per_sample;
             tc_epilogue(p, tmem + (unsigned)acc * acc_cols, quad, half, lane, row0, sample, s_bias, s_estage, s_part);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-                tmbar_arrive(&s_acc_empty[acc]);   // one arrival per epilogue warp
-                if (p.done != nullptr) red_release_gpu(p.done + sample);   // this warp's rows (and sums) of the tile are out
-            }
+            __syncwarp();   // (also orders every lane's stores of this tile before lane 0's later release)
+            if (lane == 0) tmbar_arrive(&s_acc_empty[acc]);   // one arrival per epilogue warp
+            if (p.done != nullptr) unsignalled = sample;
             TC_MARK(threadIdx.x == 320 && ti < 4, 28 + ti);
         }
+        if (unsignalled >= 0 && lane == 0) red_release_gpu(p.done + unsignalled);
     }
     __syncwarp();   // the producer / MMA roles run on one lane: re-converge those warps before the CTA-wide barrier
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

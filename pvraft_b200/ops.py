@@ -186,7 +186,7 @@ def linear(x, weight, bias=None, *, cin=None, w_ld=0, w_cin=0, in_mode=IN_PLAIN,
 
 _TC_WEIGHTS = {}
 _EARLY_PARAMS = os.environ.get('PVRAFT_TC_EARLY_PARAMS', '1') != '0'
-_CHAIN = os.environ.get('PVRAFT_TC_CHAIN', '1') != '0'
+_CHAIN = os.environ.get('PVRAFT_TC_CHAIN', '0') == '1'   # opt-in: see tc_linear(chain=...)
 TC_PLAIN, TC_GRU_ZR, TC_GRU_Q, TC_FLOW = 0, 1, 2, 3
 
 
@@ -323,7 +323,8 @@ def tc_linear(sources, w, bias=None, *, in_min=None, in_stats=None, in_gamma=Non
     prev = getattr(_TLS, 'last_tc', None)
     # chain only on the launch that directly precedes this one (no other library launch in between), same tiling
     # (worth it only when CTAs walk several tiles: with one tile per CTA the per-sample spin costs more than the grid-wide
-    #  wait it replaces -- measured -1.7 % at B=2, N=8192 = 128 tiles, +0.8 % at 512 tiles)
+    #  wait it replaces -- measured -1.7 % at B=2, N=8192 = 128 tiles, +0.8 % at 512 tiles with eager launches and nothing
+    #  under graph replay, which is why it is opt-in, PVRAFT_TC_CHAIN=1)
     chained = (chain and done is not None and prev is not None and prev[0] == launch_count and prev[1] is not None
                and prev[2] == (b, n) and bool(a.params_settled) and b * n // 128 > _sm_count())
     if chained:

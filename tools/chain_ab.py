@@ -11,6 +11,7 @@ from pvraft_b200 import RSF  # noqa: E402
 dev = torch.device('cuda:0')
 torch.manual_seed(0)
 model = RSF(bench.make_args()).to(dev).eval()
+model.use_cuda_graph = False   # the comparison is about eager launches
 pc1, pc2 = [t.to(dev) for t in bench.synthetic_clouds(8, bench.N_POINTS, 1234)]
 with torch.no_grad():
     for _ in range(4):
@@ -22,4 +23,4 @@ with torch.no_grad():
         out = model([pc1, pc2], 32)[-1]
     e1.record()
     torch.cuda.synchronize()
-print('chain', os.environ.get('PVRAFT_TC_CHAIN', '1'), 'ms/forward', e0.elapsed_time(e1) / 10, 'checksum', float(out.double().abs().sum()))
+print('chain', os.environ.get('PVRAFT_TC_CHAIN', '0'), 'ms/forward', e0.elapsed_time(e1) / 10, 'checksum', float(out.double().abs().sum()))

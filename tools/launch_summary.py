@@ -1,19 +1,23 @@
-"""Per-kernel totals of an ncu launch list (`ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file X ...`).
-python tools/launch_summary.py X.csv [rows]"""
+"""Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel."""
 import collections
 import csv
+import re
 import sys
 
-rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10]
-hdr = rows[0]
-ki, vi, ui = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
+lines = [l for l in open(sys.argv[1]) if not l.startswith('==')]
 agg = collections.defaultdict(lambda: [0, 0.0])
-for r in rows[1:]:
-    v = float(r[vi].replace(',', ''))
-    v = v / 1e3 if r[ui] == 'ns' else v * 1e3 if r[ui] == 'ms' else v
-    agg[r[ki][:60]][0] += 1
-    agg[r[ki][:60]][1] += v
-tot = sum(v[1] for v in agg.values())
-print('total us', tot, 'launches', sum(v[0] for v in agg.values()))
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:int(sys.argv[2]) if len(sys.argv) > 2 else 16]:
-    print(f'{v[1]:10.1f} us {100 * v[1] / tot:5.1f}% n={v[0]:4d} avg={v[1] / v[0]:8.1f}  {k}')
+tot = 0.0
+for row in csv.DictReader(lines):
+    try:
+        v = float(row['Metric Value'].replace(',', ''))
+    except (ValueError, KeyError):
+        continue
+    unit = row['Metric Unit']
+    v = v / 1e3 if unit in ('ns', 'nsecond') else v * 1e3 if unit in ('ms', 'msecond') else v
+    name = re.sub(r'\(.*', '', row['Kernel Name'])[:60]
+    agg[name][0] += 1
+    agg[name][1] += v
+    tot += v
+print(f'total {tot:.1f} us over {sum(c for c, _ in agg.values())} launches')
+for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:int(sys.argv[2]) if len(sys.argv) > 2 else 20]:
+    print(f'{t:10.1f} us {100 * t / tot:5.1f}% n={c:4d} avg={t / c:8.1f}  {k}')

@@ -19,6 +19,7 @@ a = ap.parse_args()
 dev = torch.device('cuda:0')
 torch.manual_seed(0)
 model = RSF(bench.make_args()).to(dev).eval()
+model.use_cuda_graph = False   # per-launch profiling needs the eager launch sequence
 pc1, pc2 = [t.to(dev) for t in bench.synthetic_clouds(a.batch, bench.N_POINTS, 1234)]
 with torch.no_grad():
     for _ in range(a.warm):
