@@ -381,6 +381,34 @@ def run_native(a):
     if rank != 0:
         return None
     cpu = gpu_ref = None
+
+    def assemble():
+        return {
+            'metric': 'raft_sample_iters_per_sec', 'value': value, 'unit': 'sample-iterations/s', 'n_gpus': world,
+            'steps': a.steps, 'warmup': max(a.warmup, 3), 'ms_per_step': ms / a.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': a.dtype, 'data': 'synthetic',
+            'config': workload_config(B, world, iters, graphed, a.refine, a.dtype),
+            'e2e': {'value': e2e, 'unit': 'sample-iterations/s', 'h2d_bytes_per_step': 2 * B * N_POINTS * 3 * 4 * world,
+                    'd2h_bytes_per_step': B * N_POINTS * 3 * 4 * world, 'ms_per_step': ms_e2e / a.steps},
+            'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'gpu_reference': gpu_ref,
+        }
+
+    # The measurement proper is complete here.  The two baseline legs below run foreign code (torch CPU / torch eager ops of
+    # the oracle) for ~25 s and ~2 s; if one of them ever stalls (an oversubscribed host, a wedged OpenMP team), the line is
+    # still printed -- with that leg marked unavailable -- instead of the whole run being lost.
+    legs_done = threading.Event()
+
+    def watchdog(limit_s=float(os.environ.get('PVRAFT_BENCH_LEG_LIMIT', '420'))):
+        if legs_done.wait(limit_s):
+            return
+        nonlocal cpu, gpu_ref
+        note = {'unavailable': f'baseline leg did not finish within {limit_s:.0f} s'}
+        cpu = cpu if cpu is not None else dict(note, value=None, unit='sample-iterations/s', cores=None, kind='port', sample='none')
+        gpu_ref = gpu_ref if gpu_ref is not None else note
+        _emit_and_exit(assemble())
+
+    if world == 1 and not (a.no_cpu and (a.no_gpu_ref or a.refine)):
+        threading.Thread(target=watchdog, daemon=True).start()
     if world == 1 and not a.no_cpu:
         threads = cpu_pick_threads()
         tp, tl = cpu_sample(threads)
@@ -397,15 +425,8 @@ def run_native(a):
                        'speedup': value / (B * iters / t_ref)}
         except Exception as e:   # noqa: BLE001  (out of memory on a smaller device: report, do not fail the bench)
             gpu_ref = {'unavailable': f'{type(e).__name__}: {e}'[:200]}
-    line = {
-        'metric': 'raft_sample_iters_per_sec', 'value': value, 'unit': 'sample-iterations/s', 'n_gpus': world,
-        'steps': a.steps, 'warmup': max(a.warmup, 3), 'ms_per_step': ms / a.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': a.dtype, 'data': 'synthetic',
-        'config': workload_config(B, world, iters, graphed, a.refine, a.dtype),
-        'e2e': {'value': e2e, 'unit': 'sample-iterations/s', 'h2d_bytes_per_step': 2 * B * N_POINTS * 3 * 4 * world,
-                'd2h_bytes_per_step': B * N_POINTS * 3 * 4 * world, 'ms_per_step': ms_e2e / a.steps},
-        'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu, 'gpu_reference': gpu_ref,
-    }
+    legs_done.set()
+    line = assemble()
     return line
 
 
@@ -543,6 +564,16 @@ def run_train(a):
     }
 
 
+_SAVED_STDOUT = [None]
+
+
+def _emit_and_exit(line):
+    """Print the JSON line on the real stdout (fd 1 is routed to stderr while the benchmark runs) and leave."""
+    fd = _SAVED_STDOUT[0] if _SAVED_STDOUT[0] is not None else 1
+    os.write(fd, (json.dumps(line) + '\n').encode())
+    os._exit(0)
+
+
 class _QuietStdout:
     """Libraries (NCCL's version banner, warnings) write to fd 1; the contract is ONE JSON line on stdout.
     Route fd 1 to stderr while the benchmark runs and restore it for the final print."""
@@ -550,6 +581,7 @@ class _QuietStdout:
     def __enter__(self):
         sys.stdout.flush()
         self.saved = os.dup(1)
+        _SAVED_STDOUT[0] = self.saved
         os.dup2(2, 1)
         return self
 
@@ -557,6 +589,7 @@ class _QuietStdout:
         sys.stdout.flush()
         os.dup2(self.saved, 1)
         os.close(self.saved)
+        _SAVED_STDOUT[0] = None
 
 
 def main():
