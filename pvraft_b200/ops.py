@@ -190,14 +190,15 @@ _CHAIN = os.environ.get('PVRAFT_TC_CHAIN', '0') == '1'   # opt-in: see tc_linear
 TC_PLAIN, TC_GRU_ZR, TC_GRU_Q, TC_FLOW = 0, 1, 2, 3
 
 
-def tc_weights(weights, col0=0, cols=None, k_pad=None, kcat=False):
+def tc_weights(weights, col0=0, cols=None, k_pad=None, kcat=False, transposed=None):
     """tf32 hi/lo split of a (stack of) [cout, cin(,1,1)] weight(s) -> (hi, lo) [n_pad, k_pad], cached per parameter
-    version (inference weights are static, so this runs once)."""
+    version (inference weights are static, so this runs once; the training path re-splits after every optimizer step).
+    transposed=(r0, r1): the split of W^T[r0:r1, :] instead -- the operand of dx = dy . W for input columns r0..r1."""
     if torch.is_tensor(weights):
         weights = (weights,)
     # keyed by the identity of the source tensor OBJECTS (validated through weak references and version counters):
     # a data_ptr key would go stale when the allocator hands a freed weight's address to a new tensor
-    key = tuple(id(w) for w in weights) + (col0, cols, k_pad, kcat)
+    key = tuple(id(w) for w in weights) + (col0, cols, k_pad, kcat, transposed)
     hit = _TC_WEIGHTS.get(key)
     if hit is not None:
         refs, versions, ptrs, result = hit
@@ -205,6 +206,8 @@ def tc_weights(weights, col0=0, cols=None, k_pad=None, kcat=False):
             return result
     _TLS.unsettled = 3   # the split below writes what the next tensor-core launches read: see tc_linear()
     mats = [w.detach().reshape(w.shape[0], -1) for w in weights]
+    if transposed is not None:
+        mats = [m.t()[transposed[0]:transposed[1]].contiguous() for m in mats]
     if kcat:   # [W_a | W_b | ...] along K: one GEMM over concatenated sources adds the layers' outputs
         mats = [torch.cat(mats, 1).contiguous()]
     ld = mats[0].shape[1]
@@ -212,8 +215,10 @@ def tc_weights(weights, col0=0, cols=None, k_pad=None, kcat=False):
     kp = (ncols + 31) // 32 * 32 if k_pad is None else k_pad
     rows = sum(m.shape[0] for m in mats)
     n_pad = (rows + 15) // 16 * 16
-    hi = torch.zeros(n_pad, kp, dtype=torch.float32, device=mats[0].device)
-    lo = torch.zeros_like(hi)
+    # (the split kernel writes every entry of the rows it is given, padding columns included: zero-fill only for padding rows)
+    alloc = torch.empty if n_pad == rows else torch.zeros
+    hi = alloc(n_pad, kp, dtype=torch.float32, device=mats[0].device)
+    lo = alloc(n_pad, kp, dtype=torch.float32, device=mats[0].device)
     r0 = 0
     for m in mats:
         check(lib().pvraft_tc_weight_split(_p(m.contiguous()), m.shape[0], ncols, ld, col0, m.shape[0], kp,

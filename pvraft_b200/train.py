@@ -19,6 +19,8 @@ writes as single ATen calls (cat / split / relu / sigmoid / tanh / add / mul on 
 every iteration (model/RAFTSceneFlow.py:41) and derives every index under no_grad (model/corr.py:52-62).
 All tensors are point-major [B,rows,C] (rows = N per-point, N*32 per-edge).
 """
+import os
+
 import torch
 
 from . import ops
@@ -30,6 +32,16 @@ def _zeros64(*shape, device):
     return torch.zeros(*shape, dtype=torch.float64, device=device)
 
 
+# Per-point layers of the training path on the tcgen05 kernel: 'auto' = while the step is being captured into a CUDA graph
+# (26.9 vs 30.0 ms per step); with eager launches the host cost of the tensor-core launch path (tensor-map encodes, the weight
+# splits after every optimizer step) outweighs the faster kernels (40.5 vs 33.0 ms), so there the CUDA-core kernels stay.
+_TC_TRAIN = os.environ.get('PVRAFT_TC_TRAIN', 'auto')
+
+
+def _tc_train():
+    return _TC_TRAIN == '1' or (_TC_TRAIN == 'auto' and torch.cuda.is_current_stream_capturing())
+
+
 class LinearFn(torch.autograd.Function):
     """y[B,R,cout] = x[B,R,cin] . W^T (+ b); optionally also the GroupNorm sums [B,8,2] of y (not differentiable: the
     consumer GnActFn differentiates through the statistics itself)."""
@@ -39,7 +51,15 @@ class LinearFn(torch.autograd.Function):
         w2 = w.reshape(w.shape[0], -1).contiguous()
         x = x.contiguous()
         stats = _zeros64(x.shape[0], 8, 2, device=x.device) if want_stats else None
-        y = ops.linear(x, w2, b, out_stats=stats)
+        cout, cin = w2.shape
+        # per-point layers whose shapes fit go to the tcgen05 kernel (3xTF32: fp32-accurate), forward and dx; the weight is
+        # split once per parameter version, i.e. once per optimizer step however many iterations use the layer
+        ctx.tc = _tc_train() and x.dim() == 3 and ops.tc_supported(x.shape[1], cin) and cout <= 128 and (not want_stats or cout % 32 == 0)
+        ctx.w_ref = w
+        if ctx.tc:
+            y = ops.tc_linear([x], ops.tc_weights(w), None if b is None else b.detach(), out_stats=stats)
+        else:
+            y = ops.linear(x, w2, b, out_stats=stats)
         ctx.save_for_backward(x, w2)
         ctx.has_bias, ctx.w_shape = b is not None, w.shape
         if want_stats:
@@ -60,8 +80,11 @@ class LinearFn(torch.autograd.Function):
             return dx, dw.reshape(ctx.w_shape), db, None
         if ctx.needs_input_grad[0]:
             # dx = dy . W: the same kernel with the transposed weight, 128 output columns (the kernel's limit) at a time
-            cin = w2.shape[1]
-            parts = [ops.linear(dy, w2[:, c0:min(c0 + 128, cin)].t().contiguous()) for c0 in range(0, cin, 128)]
+            cout, cin = w2.shape
+            if ctx.tc and cout % 32 == 0:
+                parts = [ops.tc_linear([dy], ops.tc_weights(ctx.w_ref, transposed=(c0, min(c0 + 128, cin)))) for c0 in range(0, cin, 128)]
+            else:
+                parts = [ops.linear(dy, w2[:, c0:min(c0 + 128, cin)].t().contiguous()) for c0 in range(0, cin, 128)]
             dx = parts[0] if len(parts) == 1 else torch.cat(parts, -1)
         dw = db = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):

@@ -72,6 +72,42 @@ def test_linear_fn(dev, b, r, cin, cout, bias):
         assert torch.allclose(stats[..., 0].cpu(), gs.sum((1, 3)), rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize('b,r,cin,cout,bias,stats', [(2, 1024, 192, 64, True, True), (1, 2048, 64, 96, False, True),
+                                                     (2, 512, 128, 61, True, False), (1, 256, 32, 128, True, True)])
+def test_linear_fn_on_tensor_cores(dev, b, r, cin, cout, bias, stats):
+    """The per-point layers of a CAPTURED training step run on the tcgen05 kernel (3xTF32), forward and dx (PVRAFT_TC_TRAIN=auto;
+    forced here): same Function, same bounds as the CUDA-core path."""
+    from pvraft_b200 import ops, train as T
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    x, w = torch.randn(b, r, cin, generator=g), torch.randn(cout, cin, 1, generator=g) / cin ** 0.5
+    bv = torch.randn(cout, generator=g) if bias else None
+    gy = torch.randn(b, r, cout, generator=g)
+    xr, wr, br = leaf(x).double(), leaf(w).double(), (leaf(bv).double() if bias else None)
+    xr.retain_grad(); wr.retain_grad()
+    if bias:
+        br.retain_grad()
+    yr = F.linear(xr, wr.reshape(cout, cin), br)
+    yr.backward(gy.double())
+    xd, wd, bd = leaf(x, dev), leaf(w, dev), (leaf(bv, dev) if bias else None)
+    was, n0 = T._TC_TRAIN, ops.launch_count
+    T._TC_TRAIN = '1'
+    try:
+        out = T.linear(xd, wd, bd, stats)
+        y, st = out if stats else (out, None)
+        y.backward(gy.to(dev))
+    finally:
+        T._TC_TRAIN = was
+    assert rel_err(y.detach().cpu(), yr.detach()) < 1e-5
+    assert rel_err(xd.grad.cpu(), xr.grad) < 2e-5
+    assert rel_err(wd.grad.cpu(), wr.grad) < 5e-5
+    if bias:
+        assert rel_err(bd.grad.cpu(), br.grad) < 5e-5
+    if st is not None:
+        gs = yr.detach().reshape(b, r, 8, cout // 8)
+        assert torch.allclose(st[..., 0].cpu(), gs.sum((1, 3)), rtol=1e-5, atol=1e-3)
+        assert torch.allclose(st[..., 1].cpu(), (gs ** 2).sum((1, 3)), rtol=1e-5, atol=1e-2)
+
+
 @pytest.mark.parametrize('b,r,c,act', [(2, 512, 64, 'lrelu'), (1, 3000, 16, 'lrelu'), (2, 640, 48, 'lrelu'), (1, 2048, 128, 'prelu'),
                                        (2, 96, 96, 'none')])
 def test_gn_act_fn(dev, b, r, c, act):
@@ -328,6 +364,29 @@ def test_training_steps_like_the_engine(dev):
         Wn = {kk: v.detach().cpu() for kk, v in m.state_dict().items()}
         want = O.rsf_forward(Wn, pc1.cpu(), pc2.cpu(), 2, 3, 0.25, 64)
     assert float((ev[-1].cpu() - want[-1]).abs().mean()) < 1e-2 * float(want[-1].abs().mean())
+
+
+def test_whole_model_gradients_with_tensor_core_layers(dev):
+    """The same training step with the per-point layers on the tcgen05 kernel (what a captured step runs) and on the CUDA-core
+    kernels: all 95 gradients agree (both are fp32-accurate; N = 1024 so that the tensor-core shapes apply)."""
+    from pvraft_b200 import RSF, train as T
+    args = types.SimpleNamespace(corr_levels=3, base_scales=0.25, truncate_k=128)
+    torch.manual_seed(0)
+    m = RSF(args).to(dev).train()
+    pc1, pc2 = [t.to(dev) * 0.4 for t in O.synthetic_clouds(2, 1024, seed=9)]
+    gt = pc2 - pc1
+    grads = {}
+    was = T._TC_TRAIN
+    try:
+        for mode in ('0', '1'):
+            T._TC_TRAIN = mode
+            m.zero_grad(set_to_none=True)
+            sequence_loss(m([pc1, pc2], num_iters=3), gt).backward()
+            grads[mode] = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    finally:
+        T._TC_TRAIN = was
+    assert len(grads['1']) == 95
+    compare_grads(grads['1'], {k: v.cpu() for k, v in grads['0'].items()}, 2e-2, 5e-2)
 
 
 def test_device_side_loss_and_metrics(dev):
