@@ -25,7 +25,7 @@ import torch
 
 from . import ops
 from .graph import Graph
-from .ops import ACT_LRELU, ACT_NONE, ACT_RELU
+from .ops import ACT_LRELU
 
 
 def _zeros64(*shape, device):

@@ -1,6 +1,5 @@
 """Pin the CPU oracle (oracle/pvraft_oracle.py) against golden vectors produced by the unmodified
 reference (tests/golden/make_golden.py).  CPU only."""
-import numpy as np
 import pytest
 import torch
 

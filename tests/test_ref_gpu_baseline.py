@@ -4,7 +4,6 @@ ATen op sequence, model/corr.py + model/update.py + model/flot/*) on the B200 it
 travel to the GPU box; its formulation can.  Writes gpurun_out/ref_gpu_baseline.json (copied to profiles/)."""
 import json
 import os
-import time
 
 import pytest
 import torch
